@@ -1,0 +1,112 @@
+/*
+ * knn_b200 - B200-native exact (flat) k-nearest-neighbour engine: C ABI.
+ *
+ * Drop-in boundary for the one hot path of konstin/knn-for-homology: the calls its Python
+ * drivers make into faiss-cpu (SWIG) for flat search.  There is no plugin/FFI registry in
+ * the reference; the "operator API" is the faiss Python surface itself, so every entry
+ * point below names the faiss call it replaces and the reference call sites
+ * (paths relative to /root/reference).  The Python binding a maintainer would add is the
+ * ctypes stub in knn-for-homology_b200/knn_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; row-major, C-contiguous matrices;
+ *   - every function returns 0 on success, a negative KNN_ERR_* otherwise, and leaves a
+ *     message retrievable with knn_last_error() (thread-local);
+ *   - "host" entry points take host pointers (pageable or pinned), do their own H2D/D2H
+ *     copies and return when the result is in the caller's buffers;
+ *   - "_dev" entry points take device pointers of the index's device, enqueue on the
+ *     cudaStream_t passed as `stream` (NULL = default stream) and may synchronise it;
+ *   - the caller owns all buffers; `add` copies (faiss semantics: the drivers reuse and
+ *     mutate their arrays after add, pfam/proteins_search.py:37,49);
+ *   - the library is CUDA-only: it fails with KNN_ERR_CUDA when no sm_100 device is
+ *     usable; there is no CPU fallback.
+ */
+#ifndef KNN_B200_H
+#define KNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KNN_METRIC_INNER_PRODUCT 0 /* faiss.METRIC_INNER_PRODUCT (cath/search.py:31) */
+#define KNN_METRIC_L2 1            /* faiss.METRIC_L2            (cath/search.py:32) */
+
+#define KNN_OK 0
+#define KNN_ERR_INVALID (-1) /* bad argument (NULL, shape, k <= 0, ...) */
+#define KNN_ERR_CUDA (-2)    /* CUDA runtime / driver failure, or no usable device */
+#define KNN_ERR_MEMORY (-3)  /* device or host allocation failed */
+#define KNN_ERR_LIMIT (-4)   /* a documented limit was exceeded (k > KNN_MAX_K, ids >= 2^32) */
+
+#define KNN_MAX_K 2048 /* reference uses k in {5,10,11,13,500,1000,2000} */
+
+/* knn_index_create flags */
+#define KNN_FLAG_BF16_STORAGE 1u /* keep only bf16 rows (the bf16 values ARE the database; config C5) */
+
+typedef struct knn_index knn_index;
+
+/* Message of the last error on the calling thread ("" if none). */
+const char* knn_last_error(void);
+
+/* Number of CUDA devices visible (0 if CUDA cannot be initialised). */
+int knn_device_count(void);
+
+/* faiss.normalize_L2(x): in-place x[i] *= 1/sqrt(sum x[i]^2), zero rows untouched.
+ * Call sites: cath/search.py:19, pfam/proteins_search.py:22, seqvec_search/main.py:31,34,
+ * pfam/search.py:18,20, pfam/slices/slices_search.py:18. */
+int knn_normalize_l2(float* x, int64_t n, int64_t d, int device);
+int knn_normalize_l2_dev(float* x_dev, int64_t n, int64_t d, void* stream);
+
+/* faiss.IndexFlat(d, metric) - cath/search.py:20, pfam/proteins_search.py:24,
+ * seqvec_search/main.py:35.  `device` = CUDA ordinal. */
+int knn_index_create(knn_index** out, int d, int metric, int device, unsigned flags);
+int knn_index_free(knn_index* idx);
+/* faiss Index::reset(): drop all rows, keep d/metric. */
+int knn_index_reset(knn_index* idx);
+/* Optional: pre-size the device storage for n rows in total (avoids regrowth copies). */
+int knn_index_reserve(knn_index* idx, int64_t n);
+
+/* index.add(xb) - cath/search.py:22, pfam/proteins_search.py:37, seqvec_search/main.py:39.
+ * Appends n rows; ids are the implicit row numbers 0..ntotal-1. */
+int knn_index_add(knn_index* idx, int64_t n, const float* x);
+int knn_index_add_dev(knn_index* idx, int64_t n, const float* x_dev, void* stream);
+
+int64_t knn_index_ntotal(const knn_index* idx);
+int knn_index_d(const knn_index* idx);
+int knn_index_metric(const knn_index* idx);
+
+/* index.search(xq, k) -> (D, I) - cath/search.py:24, pfam/proteins_search.py:49,
+ * seqvec_search/main.py:45.  D: (nq,k) float32, I: (nq,k) int64, best first (IP: largest,
+ * L2: smallest squared distance, computed as |x|^2+|y|^2-2<x,y> clamped at 0).  Equal scores:
+ * lower id first.  k > ntotal: tail padded with id -1 and -FLT_MAX (IP) / +FLT_MAX (L2).
+ * `id_base` (dev variant) is added to every returned id: a shard of a row-sharded database
+ * returns global row numbers. */
+int knn_index_search(knn_index* idx, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I);
+int knn_index_search_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, float* D_dev,
+                         int64_t* I_dev, int64_t id_base, void* stream);
+
+/* Copy rows [i0, i0+n) back to the host as float32 (faiss Index::reconstruct_n); feeds
+ * write_index (pfam/proteins_search.py:39-40). */
+int knn_index_reconstruct(knn_index* idx, int64_t i0, int64_t n, float* out);
+
+/* Cross-shard merge (new; the reference is single-process): `nlists` sorted (D, I) results of
+ * shape (nq,k), laid out [list][nq][k] in device memory (e.g. the output of an NCCL
+ * all-gather), are merged per query into the best k, same ordering rules as search. */
+int knn_merge_topk_dev(int metric, int64_t nq, int64_t k, int nlists, const float* D_lists_dev,
+                       const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev, void* stream);
+
+/* Tuning / introspection.  Parameters: "path" (0 auto, 1 exact fp32 scan, 2 tensor-core
+ * filter + rerank), "query_batch", "profile" (1: time the dominant kernel with CUDA events).
+ * Statistics of the last search: "path", "launches", "gemm_launches", "gemm_ms",
+ * "candidates", "overflow_batches", "rerank_pairs". */
+int knn_index_set_param(knn_index* idx, const char* name, int64_t value);
+int knn_index_get_stat(const knn_index* idx, const char* name, double* out);
+
+/* Total number of kernels this library has launched in this process. */
+int64_t knn_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KNN_B200_H */

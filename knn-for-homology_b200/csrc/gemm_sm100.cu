@@ -1,0 +1,423 @@
+// Distance GEMM with a fused threshold-filter epilogue for sm_100a: TMA (128-byte swizzle) ->
+// shared memory -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld -> compare against
+// the per-query candidate threshold -> rare append to the per-query candidate list.  The
+// nq x N score matrix never reaches HBM.
+//
+// This is the one dense contraction of the flat-search path: the `sgemm` inside faiss's
+// knn_inner_product / knn_L2sqr behind index.search (reference call sites cath/search.py:24,
+// pfam/proteins_search.py:49, seqvec_search/main.py:45; faiss itself is third-party, see
+// oracle/flat_oracle.py).  Scores produced here are approximate (bf16 inputs); the candidate
+// threshold carries the error bound and the survivors are rescored in fp32 (rerank_kernel).
+//
+// Tile: 128 queries (MMA M, TMEM lanes) x 256 database rows (MMA N, TMEM columns) x 64 (one
+// 128-byte swizzle atom of K per pipeline stage).  Warp roles: 0 = TMA producer, 1 = MMA issuer
+// (+ TMEM allocator), 2..5 = epilogue (one TMEM lane quarter each).  Persistent CTAs, static
+// tile schedule with the query tile fastest so that co-resident CTAs share database tiles in L2.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace knn {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 192;
+constexpr uint32_t kBytesA = BM * BK * 2;
+constexpr uint32_t kBytesB = BN * BK * 2;
+constexpr uint32_t kBytesStage = kBytesA + kBytesB;
+constexpr size_t kSmemBytes = size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x 256 x 16 bf16 MMA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows are 128 B apart, 8-row groups
+// (one swizzle atom, 1024 B) are contiguous -> stride byte offset 1024; the leading byte offset
+// is unused for swizzled K-major layouts.  Bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
+// [46,48) version = 1 (sm_100), [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr & 0x3FFFF) >> 4);
+    d |= uint64_t(1) << 16;
+    d |= uint64_t(1024 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+
+struct __align__(8) Barriers {
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t acc_full[kAccStages];
+    uint64_t acc_empty[kAccStages];
+    uint32_t tmem_base;
+};
+
+struct GemmArgs {
+    int64_t nq;        // real queries (rows >= nq of the padded query matrix are ignored)
+    int m_tiles;       // nq_pad / 128
+    int n_tiles;       // ceil((j1 - j0) / 256)
+    int num_kb;        // dp / 64
+    int64_t j0, j1;    // database rows of this panel
+    const float* ynorm2;
+    float* thr;
+    int* counts;
+    float* cand_scores;
+    uint32_t* cand_ids;
+    int cap;
+};
+
+template <bool L2, bool DENSE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + size_t(kStages) * kBytesStage);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = args.m_tiles * args.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_q);
+        prefetch_tmap(&map_db);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&bars->full[i], 1);
+            mbar_init(&bars->empty[i], 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&bars->acc_full[i], 1);
+            mbar_init(&bars->acc_empty[i], 4);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile % args.m_tiles;
+                const int nt = tile / args.m_tiles;
+                const int row_q = mt * BM;
+                const int row_db = int(args.j0) + nt * BN;
+                for (int kb = 0; kb < args.num_kb; ++kb) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + size_t(stage) * kBytesStage;
+                    uint8_t* sb = sa + kBytesA;
+                    mbar_expect_tx(&bars->full[stage], kBytesStage);
+                    tma_load_2d(sa, &map_q, &bars->full[stage], kb * BK, row_q);
+                    tma_load_2d(sb, &map_db, &bars->full[stage], kb * BK, row_db);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
+                for (int kb = 0; kb < args.num_kb; ++kb) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + size_t(stage) * kBytesStage);
+                    const uint32_t sb = sa + kBytesA;
+                    const uint64_t da = make_smem_desc(sa);
+                    const uint64_t db = make_smem_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
+                        umma_bf16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&bars->empty[stage]);  // smem slot reusable once these MMAs have read it
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&bars->acc_full[acc]);  // accumulator complete -> epilogue
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile % args.m_tiles;
+            const int nt = tile / args.m_tiles;
+            const int64_t q = int64_t(mt) * BM + quarter * 32 + lane;
+            const int64_t jbase = args.j0 + int64_t(nt) * BN;
+            const bool q_ok = q < args.nq;
+            const float thr = q_ok ? args.thr[q] : FLT_MAX;
+            mbar_wait(&bars->acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
+#pragma unroll 1
+            for (int cg = 0; cg < BN / 32; ++cg) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + uint32_t(cg * 32), r);
+                tmem_ld_wait();
+                const int64_t j_first = jbase + cg * 32;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = __uint_as_float(r[i]);
+                    if (L2) {
+                        const int64_t j = j_first + i;
+                        v[i] = 2.0f * v[i] - (j < args.j1 ? __ldg(args.ynorm2 + j) : 0.f);
+                    }
+                }
+                if (DENSE) {
+                    if (q_ok) {
+                        float* cs = args.cand_scores + q * int64_t(args.cap) + (j_first - args.j0);
+                        uint32_t* ci = args.cand_ids + q * int64_t(args.cap) + (j_first - args.j0);
+                        if (j_first + 32 <= args.j1) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                *reinterpret_cast<float4*>(cs + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                *reinterpret_cast<uint4*>(ci + i) = make_uint4(uint32_t(j_first + i), uint32_t(j_first + i + 1),
+                                                                               uint32_t(j_first + i + 2), uint32_t(j_first + i + 3));
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                if (j_first + i < args.j1) {
+                                    cs[i] = v[i];
+                                    ci[i] = uint32_t(j_first + i);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    bool any = false;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) any |= (v[i] >= thr);
+                    if (any) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (v[i] >= thr && j_first + i < args.j1) {
+                                const int pos = atomicAdd(args.counts + q, 1);
+                                if (pos < args.cap) {
+                                    args.cand_scores[q * int64_t(args.cap) + pos] = v[i];
+                                    args.cand_ids[q * int64_t(args.cap) + pos] = uint32_t(j_first + i);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();  // reconverge before the next warp-wide tcgen05.ld
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct GemmPlan {
+    EncodeTiledFn encode = nullptr;
+    int sms = 148;
+    bool attrs_set = false;
+};
+
+int gemm_plan_create(GemmPlan** out, int device) {
+    GemmPlan* p = new GemmPlan();
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        delete p;
+        return KNN_ERR_CUDA;
+    }
+    p->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    int major = 0;
+    cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) {
+        set_error("the tensor-core path needs an sm_100 device (found compute capability %d.x)", major);
+        delete p;
+        return KNN_ERR_CUDA;
+    }
+    *out = p;
+    return KNN_OK;
+}
+
+void gemm_plan_destroy(GemmPlan* p) { delete p; }
+
+static int make_map(GemmPlan* p, CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int dp, int box_rows) {
+    cuuint64_t gdim[2] = {cuuint64_t(dp), cuuint64_t(rows)};
+    cuuint64_t gstride[1] = {cuuint64_t(dp) * 2};
+    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = p->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld, dp=%d)", int(r), (long long)rows, dp);
+        return KNN_ERR_CUDA;
+    }
+    return KNN_OK;
+}
+
+int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, int64_t nq_pad, int dp,
+                       const __nv_bfloat16* xb_bf16, int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1,
+                       int metric, bool dense_first, FilterState st, cudaStream_t s) {
+    if (j1 <= j0 || nq <= 0) return KNN_OK;
+    if (dp % BK != 0 || nq_pad % BM != 0) {
+        set_error("gemm_filter: dp (%d) must be a multiple of %d and nq_pad (%lld) of %d", dp, BK, (long long)nq_pad, BM);
+        return KNN_ERR_INVALID;
+    }
+    if (dense_first && j1 - j0 > st.cap) {
+        set_error("gemm_filter: dense panel larger than the candidate capacity");
+        return KNN_ERR_INVALID;
+    }
+    CUtensorMap map_q, map_db;
+    KNN_CHECK(make_map(p, &map_q, xq_bf16, nq_pad, dp, BM));
+    KNN_CHECK(make_map(p, &map_db, xb_bf16, ntotal, dp, BN));
+    GemmArgs a;
+    a.nq = nq;
+    a.m_tiles = int(nq_pad / BM);
+    a.n_tiles = int((j1 - j0 + BN - 1) / BN);
+    a.num_kb = dp / BK;
+    a.j0 = j0;
+    a.j1 = j1;
+    a.ynorm2 = ynorm2;
+    a.thr = st.thr;
+    a.counts = st.counts;
+    a.cand_scores = st.cand_scores;
+    a.cand_ids = st.cand_ids;
+    a.cap = st.cap;
+    const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;
+    const int grid = int(tiles < p->sms ? tiles : p->sms);
+    const bool l2 = metric == KNN_METRIC_L2;
+    if (!p->attrs_set) {
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        p->attrs_set = true;
+    }
+    if (l2) {
+        if (dense_first) gemm_filter_kernel<true, true><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
+        else gemm_filter_kernel<true, false><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
+    } else {
+        if (dense_first) gemm_filter_kernel<false, true><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
+        else gemm_filter_kernel<false, false><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
+    }
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+}  // namespace knn

@@ -1,0 +1,608 @@
+// C ABI of libknn_b200.so and the host-side orchestration of a search.
+//
+// Replaces, for the flat path only, the faiss calls of the reference drivers (paths relative
+// to /root/reference): faiss.normalize_L2 (cath/search.py:19), faiss.IndexFlat
+// (cath/search.py:20), index.add (cath/search.py:22), index.search (cath/search.py:24,
+// pfam/proteins_search.py:49, seqvec_search/main.py:45).
+//
+// Two device paths, both CUDA only:
+//   exact  : fp32 scan kernel -> dense scores -> two-level radix select          (small nq / small N)
+//   tensor : tcgen05 bf16 GEMM with threshold-filter epilogue over growing database panels,
+//            per-panel threshold tightening, exact fp32 rerank of the surviving candidates,
+//            final radix select                                                   (large batches)
+// The tensor path returns exactly what the exact path returns: the filter keeps a provable
+// superset of the true top-k (DESIGN.md "error bound") and the rerank recomputes the scores
+// with the scan kernel's arithmetic.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace knn {
+
+static thread_local std::string g_error;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t want) {
+        if (want <= bytes) return KNN_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            return KNN_ERR_MEMORY;
+        }
+        bytes = want;
+        return KNN_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; }
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace knn
+
+using namespace knn;
+
+struct knn_index {
+    int d = 0, dp = 0, metric = 0, device = 0;
+    unsigned flags = 0;
+    int64_t ntotal = 0, capacity = 0;
+    float* xb_f32 = nullptr;          // [capacity x dp] zero-padded rows (absent with BF16_STORAGE)
+    __nv_bfloat16* xb_bf16 = nullptr; // [capacity x dp]
+    float* ynorm2 = nullptr;          // [capacity]
+    DbStats* stats = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t add_event = nullptr;  // last ingest; searches on another stream wait on it
+    GemmPlan* plan = nullptr;
+    // workspaces
+    DevBuf stage, xq_f32, xq_bf16, xnorm2, eps, thr, counts, cand_s, cand_i, scores, lists_s, lists_i, overflow;
+    DevBuf h_xq, h_D, h_I;
+    // parameters
+    int path_param = 0;
+    int64_t query_batch = 16384;
+    int profile = 0;
+    int64_t tensor_min_nq = 64, tensor_min_n = 8192;
+    // statistics of the last search
+    int last_path = 0;
+    long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_rerank_pairs = 0;
+    double st_gemm_ms = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+
+namespace {
+
+bool bf16_only(const knn_index* ix) { return (ix->flags & KNN_FLAG_BF16_STORAGE) != 0; }
+
+int grow(knn_index* ix, int64_t want_rows, bool exact = false) {
+    if (want_rows <= ix->capacity) return KNN_OK;
+    if (want_rows >= int64_t(0xFFFFFFFFll)) {
+        set_error("an index holds at most 2^32-2 rows");
+        return KNN_ERR_LIMIT;
+    }
+    int64_t cap = exact ? want_rows : ix->capacity + ix->capacity / 2;
+    if (cap < want_rows) cap = want_rows;
+    if (cap < 1024) cap = 1024;
+    // rows may have been ingested on a caller's stream: settle everything before moving them
+    KNN_CHECK_CUDA(cudaDeviceSynchronize());
+    float* nf = nullptr;
+    __nv_bfloat16* nb = nullptr;
+    float* nn = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!bf16_only(ix)) e = cudaMalloc(&nf, size_t(cap) * ix->dp * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&nb, size_t(cap) * ix->dp * sizeof(__nv_bfloat16));
+    if (e == cudaSuccess) e = cudaMalloc(&nn, size_t(cap) * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (nf) cudaFree(nf);
+        if (nb) cudaFree(nb);
+        if (nn) cudaFree(nn);
+        set_error("cannot allocate storage for %lld rows of %d floats: %s", (long long)cap, ix->dp,
+                  cudaGetErrorString(e));
+        return KNN_ERR_MEMORY;
+    }
+    if (ix->ntotal > 0) {
+        if (nf) KNN_CHECK_CUDA(cudaMemcpyAsync(nf, ix->xb_f32, size_t(ix->ntotal) * ix->dp * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(nb, ix->xb_bf16, size_t(ix->ntotal) * ix->dp * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, ix->stream));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(nn, ix->ynorm2, size_t(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
+    }
+    if (ix->xb_f32) cudaFree(ix->xb_f32);
+    if (ix->xb_bf16) cudaFree(ix->xb_bf16);
+    if (ix->ynorm2) cudaFree(ix->ynorm2);
+    ix->xb_f32 = nf;
+    ix->xb_bf16 = nb;
+    ix->ynorm2 = nn;
+    ix->capacity = cap;
+    return KNN_OK;
+}
+
+cudaEvent_t next_event(knn_index* ix) {
+    if (ix->ev_used == ix->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ix->ev_pool.push_back(e);
+    }
+    return ix->ev_pool[ix->ev_used++];
+}
+
+// ---- exact path ---------------------------------------------------------------------------
+int search_exact(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
+                 cudaStream_t s) {
+    const int largest = ix->metric == KNN_METRIC_INNER_PRODUCT;
+    const int64_t N = ix->ntotal;
+    const int seg_len = 32768;
+    const int64_t nseg = (N + seg_len - 1) / seg_len;
+    const int64_t list_ld = nseg * k;
+    // batch sizes from fixed budgets: lists <= 1 GiB, dense scores <= 512 MiB
+    int64_t qb = nq < 1024 ? nq : 1024;
+    while (qb > 8 && qb * list_ld * 8 > (int64_t(1) << 30)) qb /= 2;
+    int64_t chunk = ((int64_t(512) << 20) / (qb * 4)) / seg_len * seg_len;
+    if (chunk < seg_len) chunk = seg_len;
+    if (chunk > nseg * seg_len) chunk = nseg * seg_len;
+    KNN_CHECK(ix->xq_f32.ensure(size_t(qb) * ix->dp * sizeof(float)));
+    KNN_CHECK(ix->xnorm2.ensure(size_t(qb) * sizeof(float)));
+    KNN_CHECK(ix->eps.ensure(size_t(qb) * sizeof(float)));
+    KNN_CHECK(ix->scores.ensure(size_t(qb) * chunk * sizeof(float)));
+    KNN_CHECK(ix->lists_s.ensure(size_t(qb) * list_ld * sizeof(float)));
+    KNN_CHECK(ix->lists_i.ensure(size_t(qb) * list_ld * sizeof(uint32_t)));
+    for (int64_t q0 = 0; q0 < nq; q0 += qb) {
+        const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
+        KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb, ix->d, ix->dp, ix->xq_f32.as<float>(), nullptr,
+                                      ix->xnorm2.as<float>(), ix->eps.as<float>(), ix->stats, ix->metric, s));
+        for (int64_t j0 = 0; j0 < N; j0 += chunk) {
+            const int64_t j1 = j0 + chunk < N ? j0 + chunk : N;
+            KNN_CHECK(launch_scan_f32(ix->xq_f32.as<float>(), ix->xnorm2.as<float>(), nb, ix->dp, ix->xb_f32,
+                                      ix->xb_bf16, ix->ynorm2, j0, j1, ix->metric, ix->scores.as<float>(), chunk, s));
+            KNN_CHECK(launch_select_dense(ix->scores.as<float>(), chunk, j1 - j0, nb, seg_len, uint32_t(j0), k, largest,
+                                          ix->lists_s.as<float>(), ix->lists_i.as<uint32_t>(), list_ld,
+                                          (j0 / seg_len) * k, s));
+        }
+        KNN_CHECK(launch_select_final(ix->lists_s.as<float>(), ix->lists_i.as<uint32_t>(), nullptr, list_ld, list_ld,
+                                      nb, k, largest, D + q0 * k, I + q0 * k, id_base, s));
+    }
+    return KNN_OK;
+}
+
+// ---- tensor path --------------------------------------------------------------------------
+int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
+                  cudaStream_t s) {
+    const int largest = ix->metric == KNN_METRIC_INNER_PRODUCT;
+    const int64_t N = ix->ntotal;
+    int cap = 8192;
+    while (cap < 8 * k) cap *= 2;
+    const int64_t first_panel = N < cap / 2 ? N : cap / 2;
+    int64_t qb = ix->query_batch;
+    if (qb > nq) qb = nq;
+    qb = round_up(qb, 128);
+    const int64_t qpad = qb;
+    KNN_CHECK(ix->xq_f32.ensure(size_t(qpad) * ix->dp * sizeof(float)));
+    KNN_CHECK(ix->xq_bf16.ensure(size_t(qpad) * ix->dp * sizeof(__nv_bfloat16)));
+    KNN_CHECK(ix->xnorm2.ensure(size_t(qpad) * sizeof(float)));
+    KNN_CHECK(ix->eps.ensure(size_t(qpad) * sizeof(float)));
+    KNN_CHECK(ix->thr.ensure(size_t(qpad) * sizeof(float)));
+    KNN_CHECK(ix->counts.ensure(size_t(qpad) * sizeof(int)));
+    KNN_CHECK(ix->cand_s.ensure(size_t(qpad) * cap * sizeof(float)));
+    KNN_CHECK(ix->cand_i.ensure(size_t(qpad) * cap * sizeof(uint32_t)));
+    KNN_CHECK(ix->overflow.ensure(sizeof(int) * 2));
+    FilterState st;
+    st.thr = ix->thr.as<float>();
+    st.counts = ix->counts.as<int>();
+    st.cand_scores = ix->cand_s.as<float>();
+    st.cand_ids = ix->cand_i.as<uint32_t>();
+    st.cap = cap;
+    int* d_overflow = ix->overflow.as<int>();
+    if (!ix->plan) KNN_CHECK(gemm_plan_create(&ix->plan, ix->device));
+
+    for (int64_t q0 = 0; q0 < nq; q0 += qb) {
+        const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
+        const int64_t nb_pad = round_up(nb, 128);
+        KNN_CHECK_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int) * 2, s));
+        KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb_pad, ix->d, ix->dp, ix->xq_f32.as<float>(),
+                                      ix->xq_bf16.as<__nv_bfloat16>(), ix->xnorm2.as<float>(), ix->eps.as<float>(),
+                                      ix->stats, ix->metric, s));
+        KNN_CHECK(launch_init_filter(st, nb, nb_pad, int(first_panel), s));
+        int64_t j0 = 0;
+        bool first = true;
+        while (j0 < N) {
+            int64_t len = first ? first_panel : j0;  // processed rows double with every panel
+            int64_t j1 = j0 + len < N ? j0 + len : N;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (ix->profile) {
+                e0 = next_event(ix);
+                e1 = next_event(ix);
+                cudaEventRecord(e0, s);
+            }
+            KNN_CHECK(gemm_filter_launch(ix->plan, ix->xq_bf16.as<__nv_bfloat16>(), nb, nb_pad, ix->dp, ix->xb_bf16, N,
+                                         ix->ynorm2, j0, j1, ix->metric, first, st, s));
+            if (ix->profile) cudaEventRecord(e1, s);
+            ix->st_gemm_launches++;
+            KNN_CHECK(launch_tighten(st, ix->eps.as<float>(), nb, k, 1, nullptr, d_overflow, s));
+            j0 = j1;
+            first = false;
+        }
+        // thr now holds tau = (k-th best approx score) - 2 eps: rescoring everything at or above it
+        // covers the exact top-k.
+        KNN_CHECK(launch_rerank(ix->xq_f32.as<float>(), ix->xnorm2.as<float>(), nb, ix->dp, ix->xb_f32, ix->xb_bf16,
+                                ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
+        KNN_CHECK(launch_select_final(st.cand_scores, st.cand_ids, st.counts, cap, 0, nb, k, largest, D + q0 * k,
+                                      I + q0 * k, id_base, s));
+        int h_overflow[2] = {0, 0};
+        KNN_CHECK_CUDA(cudaMemcpyAsync(h_overflow, d_overflow, sizeof(h_overflow), cudaMemcpyDeviceToHost, s));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        if (h_overflow[0]) {
+            // a candidate list ran past its capacity (heavily duplicated / clustered scores):
+            // never truncate silently - redo this batch with the exact scan.
+            ix->st_overflow_batches++;
+            KNN_CHECK(search_exact(ix, nb, xq_dev + q0 * ix->d, k, D + q0 * k, I + q0 * k, id_base, s));
+        }
+    }
+    return KNN_OK;
+}
+
+int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* D, int64_t* I, int64_t id_base,
+                    cudaStream_t s) {
+    if (nq < 0 || k64 <= 0 || (nq > 0 && (!xq_dev || !D || !I))) {
+        set_error("search: invalid arguments (nq=%lld, k=%lld)", (long long)nq, (long long)k64);
+        return KNN_ERR_INVALID;
+    }
+    if (k64 > KNN_MAX_K) {
+        set_error("search: k=%lld exceeds KNN_MAX_K=%d", (long long)k64, KNN_MAX_K);
+        return KNN_ERR_LIMIT;
+    }
+    if (nq == 0) return KNN_OK;
+    KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->add_event, 0));
+    const int k = int(k64);
+    const long long launches0 = g_launches.load();
+    ix->st_gemm_launches = 0;
+    ix->st_gemm_ms = 0;
+    ix->st_overflow_batches = 0;
+    ix->ev_used = 0;
+    int rc;
+    if (ix->ntotal == 0) {
+        // nothing to search: all padding (select over an empty list)
+        KNN_CHECK(ix->lists_s.ensure(16));
+        KNN_CHECK(ix->lists_i.ensure(16));
+        rc = launch_select_final(ix->lists_s.as<float>(), ix->lists_i.as<uint32_t>(), nullptr, 0, 0, nq, k,
+                                 ix->metric == KNN_METRIC_INNER_PRODUCT, D, I, id_base, s);
+        ix->last_path = 1;
+    } else {
+        bool tensor = ix->path_param == 2 ||
+                      (ix->path_param == 0 && nq >= ix->tensor_min_nq && ix->ntotal >= ix->tensor_min_n);
+        if (tensor && ix->ntotal < k) tensor = false;
+        ix->last_path = tensor ? 2 : 1;
+        rc = tensor ? search_tensor(ix, nq, xq_dev, k, D, I, id_base, s) : search_exact(ix, nq, xq_dev, k, D, I, id_base, s);
+    }
+    if (rc != KNN_OK) return rc;
+    if (ix->profile && ix->ev_used) {
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ix->ev_pool[i], ix->ev_pool[i + 1]);
+            ix->st_gemm_ms += ms;
+        }
+    }
+    ix->st_launches = g_launches.load() - launches0;
+    return KNN_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* knn_last_error(void) { return g_error.c_str(); }
+
+int knn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t knn_kernel_launches(void) { return g_launches.load(); }
+
+int knn_normalize_l2_dev(float* x_dev, int64_t n, int64_t d, void* stream) {
+    if (n < 0 || d <= 0 || (n > 0 && !x_dev)) {
+        set_error("normalize_l2: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    return launch_normalize_l2(x_dev, n, d, static_cast<cudaStream_t>(stream));
+}
+
+int knn_normalize_l2(float* x, int64_t n, int64_t d, int device) {
+    if (n < 0 || d <= 0 || (n > 0 && !x)) {
+        set_error("normalize_l2: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    if (n == 0) return KNN_OK;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("normalize_l2: cannot select CUDA device %d (no CPU fallback)", device);
+        return KNN_ERR_CUDA;
+    }
+    // stream the matrix through a bounded device buffer
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t(256) << 20) / (d * 4));
+    float* buf = nullptr;
+    const int64_t rows_alloc = n < rows_per ? n : rows_per;
+    KNN_CHECK_CUDA(cudaMalloc(&buf, size_t(rows_alloc) * d * sizeof(float)));
+    int rc = KNN_OK;
+    for (int64_t r0 = 0; r0 < n && rc == KNN_OK; r0 += rows_per) {
+        const int64_t nr = n - r0 < rows_per ? n - r0 : rows_per;
+        cudaError_t e = cudaMemcpy(buf, x + r0 * d, size_t(nr) * d * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            rc = launch_normalize_l2(buf, nr, d, nullptr);
+            if (rc == KNN_OK) e = cudaMemcpy(x + r0 * d, buf, size_t(nr) * d * sizeof(float), cudaMemcpyDeviceToHost);
+        }
+        if (e != cudaSuccess) {
+            set_error("normalize_l2: copy failed: %s", cudaGetErrorString(e));
+            rc = KNN_ERR_CUDA;
+        }
+    }
+    cudaFree(buf);
+    return rc;
+}
+
+int knn_index_create(knn_index** out, int d, int metric, int device, unsigned flags) {
+    if (!out || d <= 0 || (metric != KNN_METRIC_INNER_PRODUCT && metric != KNN_METRIC_L2)) {
+        set_error("index_create: invalid arguments (d=%d, metric=%d)", d, metric);
+        return KNN_ERR_INVALID;
+    }
+    int ndev = knn_device_count();
+    if (device < 0 || device >= ndev) {
+        set_error("index_create: CUDA device %d not available (%d visible); this library has no CPU fallback", device, ndev);
+        return KNN_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_error("index_create: cannot select device %d", device);
+        return KNN_ERR_CUDA;
+    }
+    knn_index* ix = new knn_index();
+    ix->d = d;
+    ix->dp = int(round_up(d, kDimAlign));
+    ix->metric = metric;
+    ix->device = device;
+    ix->flags = flags;
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->add_event, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->stats, sizeof(DbStats));
+    if (e == cudaSuccess) e = cudaMemset(ix->stats, 0, sizeof(DbStats));
+    if (e != cudaSuccess) {
+        set_error("index_create: %s", cudaGetErrorString(e));
+        delete ix;
+        return KNN_ERR_CUDA;
+    }
+    *out = ix;
+    return KNN_OK;
+}
+
+int knn_index_free(knn_index* ix) {
+    if (!ix) return KNN_OK;
+    DeviceGuard g(ix->device);
+    cudaStreamSynchronize(ix->stream);
+    for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xq_bf16, &ix->xnorm2, &ix->eps, &ix->thr, &ix->counts, &ix->cand_s,
+                      &ix->cand_i, &ix->scores, &ix->lists_s, &ix->lists_i, &ix->overflow, &ix->h_xq, &ix->h_D, &ix->h_I})
+        b->release();
+    if (ix->xb_f32) cudaFree(ix->xb_f32);
+    if (ix->xb_bf16) cudaFree(ix->xb_bf16);
+    if (ix->ynorm2) cudaFree(ix->ynorm2);
+    if (ix->stats) cudaFree(ix->stats);
+    for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
+    if (ix->add_event) cudaEventDestroy(ix->add_event);
+    if (ix->plan) gemm_plan_destroy(ix->plan);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return KNN_OK;
+}
+
+int knn_index_reset(knn_index* ix) {
+    if (!ix) return KNN_ERR_INVALID;
+    DeviceGuard g(ix->device);
+    ix->ntotal = 0;
+    KNN_CHECK_CUDA(cudaMemsetAsync(ix->stats, 0, sizeof(DbStats), ix->stream));
+    KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
+    return KNN_OK;
+}
+
+int knn_index_reserve(knn_index* ix, int64_t n) {
+    if (!ix || n < 0) return KNN_ERR_INVALID;
+    DeviceGuard g(ix->device);
+    // exact size: reserve is how large databases avoid the 1.5x growth slack
+    return grow(ix, n, /*exact=*/true);
+}
+
+int knn_index_add_dev(knn_index* ix, int64_t n, const float* x_dev, void* stream) {
+    if (!ix || n < 0 || (n > 0 && !x_dev)) {
+        set_error("add: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    if (n == 0) return KNN_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    KNN_CHECK(grow(ix, ix->ntotal + n));
+    const int64_t r0 = ix->ntotal;
+    KNN_CHECK(launch_ingest(x_dev, n, ix->d, ix->dp, ix->xb_f32 ? ix->xb_f32 + r0 * ix->dp : nullptr,
+                            ix->xb_bf16 + r0 * ix->dp, ix->ynorm2 + r0, ix->stats, s));
+    KNN_CHECK_CUDA(cudaEventRecord(ix->add_event, s));
+    ix->ntotal += n;
+    return KNN_OK;
+}
+
+int knn_index_add(knn_index* ix, int64_t n, const float* x) {
+    if (!ix || n < 0 || (n > 0 && !x)) {
+        set_error("add: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    if (n == 0) return KNN_OK;
+    DeviceGuard g(ix->device);
+    KNN_CHECK(grow(ix, ix->ntotal + n));
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t(256) << 20) / (int64_t(ix->d) * 4));
+    KNN_CHECK(ix->stage.ensure(size_t(n < rows_per ? n : rows_per) * ix->d * sizeof(float)));
+    for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+        const int64_t nr = n - r0 < rows_per ? n - r0 : rows_per;
+        KNN_CHECK_CUDA(cudaMemcpyAsync(ix->stage.p, x + r0 * ix->d, size_t(nr) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+        KNN_CHECK(knn_index_add_dev(ix, nr, ix->stage.as<float>(), ix->stream));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));  // the staging buffer is reused; `add` copies (faiss semantics)
+    }
+    return KNN_OK;
+}
+
+int64_t knn_index_ntotal(const knn_index* ix) { return ix ? ix->ntotal : -1; }
+int knn_index_d(const knn_index* ix) { return ix ? ix->d : -1; }
+int knn_index_metric(const knn_index* ix) { return ix ? ix->metric : -1; }
+
+int knn_index_search_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k, float* D_dev, int64_t* I_dev,
+                         int64_t id_base, void* stream) {
+    if (!ix) {
+        set_error("search: null index");
+        return KNN_ERR_INVALID;
+    }
+    DeviceGuard g(ix->device);
+    return search_dev_impl(ix, nq, xq_dev, k, D_dev, I_dev, id_base, static_cast<cudaStream_t>(stream));
+}
+
+int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I) {
+    if (!ix || nq < 0 || k <= 0 || (nq > 0 && (!xq || !D || !I))) {
+        set_error("search: invalid arguments (nq=%lld, k=%lld)", (long long)nq, (long long)k);
+        return KNN_ERR_INVALID;
+    }
+    if (k > KNN_MAX_K) {
+        set_error("search: k=%lld exceeds KNN_MAX_K=%d", (long long)k, KNN_MAX_K);
+        return KNN_ERR_LIMIT;
+    }
+    if (nq == 0) return KNN_OK;
+    DeviceGuard g(ix->device);
+    // host batches bound the device staging buffers; each is H2D -> search -> D2H on one stream
+    const int64_t hb = 65536;
+    const int64_t nb_max = nq < hb ? nq : hb;
+    KNN_CHECK(ix->h_xq.ensure(size_t(nb_max) * ix->d * sizeof(float)));
+    KNN_CHECK(ix->h_D.ensure(size_t(nb_max) * k * sizeof(float)));
+    KNN_CHECK(ix->h_I.ensure(size_t(nb_max) * k * sizeof(int64_t)));
+    long long launches = 0, gemm_launches = 0, overflow = 0;
+    double gemm_ms = 0;
+    for (int64_t q0 = 0; q0 < nq; q0 += hb) {
+        const int64_t nb = nq - q0 < hb ? nq - q0 : hb;
+        KNN_CHECK_CUDA(cudaMemcpyAsync(ix->h_xq.p, xq + q0 * ix->d, size_t(nb) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+        KNN_CHECK(search_dev_impl(ix, nb, ix->h_xq.as<float>(), k, ix->h_D.as<float>(), ix->h_I.as<int64_t>(), 0, ix->stream));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(D + q0 * k, ix->h_D.p, size_t(nb) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(I + q0 * k, ix->h_I.p, size_t(nb) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
+        launches += ix->st_launches;
+        gemm_launches += ix->st_gemm_launches;
+        gemm_ms += ix->st_gemm_ms;
+        overflow += ix->st_overflow_batches;
+    }
+    ix->st_launches = launches;
+    ix->st_gemm_launches = gemm_launches;
+    ix->st_gemm_ms = gemm_ms;
+    ix->st_overflow_batches = overflow;
+    return KNN_OK;
+}
+
+int knn_index_reconstruct(knn_index* ix, int64_t i0, int64_t n, float* out) {
+    if (!ix || i0 < 0 || n < 0 || i0 + n > ix->ntotal || (n > 0 && !out)) {
+        set_error("reconstruct: invalid range");
+        return KNN_ERR_INVALID;
+    }
+    if (n == 0) return KNN_OK;
+    DeviceGuard g(ix->device);
+    KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
+    if (ix->xb_f32) {
+        KNN_CHECK_CUDA(cudaMemcpy2D(out, size_t(ix->d) * sizeof(float), ix->xb_f32 + i0 * ix->dp, size_t(ix->dp) * sizeof(float),
+                                    size_t(ix->d) * sizeof(float), size_t(n), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<uint16_t> tmp(size_t(n) * ix->d);
+        KNN_CHECK_CUDA(cudaMemcpy2D(tmp.data(), size_t(ix->d) * 2, ix->xb_bf16 + i0 * ix->dp, size_t(ix->dp) * 2,
+                                    size_t(ix->d) * 2, size_t(n), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) {
+            uint32_t u = uint32_t(tmp[i]) << 16;
+            memcpy(out + i, &u, 4);
+        }
+    }
+    return KNN_OK;
+}
+
+int knn_merge_topk_dev(int metric, int64_t nq, int64_t k, int nlists, const float* D_lists_dev, const int64_t* I_lists_dev,
+                       float* D_out_dev, int64_t* I_out_dev, void* stream) {
+    if (nq < 0 || k <= 0 || nlists <= 0 || (nq > 0 && (!D_lists_dev || !I_lists_dev || !D_out_dev || !I_out_dev))) {
+        set_error("merge: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    if (k > KNN_MAX_K) {
+        set_error("merge: k=%lld exceeds KNN_MAX_K=%d", (long long)k, KNN_MAX_K);
+        return KNN_ERR_LIMIT;
+    }
+    return launch_merge_lists(D_lists_dev, I_lists_dev, nlists, nq, int(k), metric == KNN_METRIC_INNER_PRODUCT, D_out_dev,
+                              I_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
+    if (!ix || !name) return KNN_ERR_INVALID;
+    std::string n(name);
+    if (n == "path" && value >= 0 && value <= 2) ix->path_param = int(value);
+    else if (n == "query_batch" && value >= 128) ix->query_batch = round_up(value, 128);
+    else if (n == "profile") ix->profile = value != 0;
+    else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
+    else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
+    else {
+        set_error("set_param: unknown parameter or bad value: %s=%lld", name, (long long)value);
+        return KNN_ERR_INVALID;
+    }
+    return KNN_OK;
+}
+
+int knn_index_get_stat(const knn_index* ix, const char* name, double* out) {
+    if (!ix || !name || !out) return KNN_ERR_INVALID;
+    std::string n(name);
+    if (n == "path") *out = ix->last_path;
+    else if (n == "launches") *out = double(ix->st_launches);
+    else if (n == "gemm_launches") *out = double(ix->st_gemm_launches);
+    else if (n == "gemm_ms") *out = ix->st_gemm_ms;
+    else if (n == "overflow_batches") *out = double(ix->st_overflow_batches);
+    else if (n == "capacity") *out = double(ix->capacity);
+    else {
+        set_error("get_stat: unknown statistic %s", name);
+        return KNN_ERR_INVALID;
+    }
+    return KNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+// CUDA-core kernels of the flat-search path: row normalisation, database ingest (fp32 master +
+// bf16 shadow + norms), query preparation, the exact fp32 scan and the exact fp32 rerank.
+// All of them are HBM-bound streaming kernels: one warp per row, 16-byte loads, grid sized
+// in multiples of the SM count.
+//
+// Reference semantics restated (no reference source exists for them: the arithmetic lives in
+// faiss-cpu 1.7.2, see oracle/flat_oracle.py):
+//   normalize_l2_kernel  <- faiss.normalize_L2        (cath/search.py:19, seqvec_search/main.py:31,34)
+//   ingest_rows_kernel   <- IndexFlat.add             (cath/search.py:22, pfam/proteins_search.py:37)
+//   scan_f32_kernel      <- IndexFlat.search, fp32    (cath/search.py:24, seqvec_search/main.py:45)
+#include "common.cuh"
+
+namespace knn {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlock = kWarpsPerBlock * 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+int grid_for_rows(int64_t rows, int rows_per_block, int blocks_per_sm) {
+    int64_t want = (rows + rows_per_block - 1) / rows_per_block;
+    int64_t cap = int64_t(num_sms()) * blocks_per_sm;
+    if (want < 1) want = 1;
+    return int(want < cap ? want : cap);
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) normalize_l2_kernel(float* __restrict__ x, int64_t n, int64_t d,
+                                                               int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = int64_t(gridDim.x) * kWarpsPerBlock;
+    for (int64_t row = int64_t(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5); row < n; row += warps) {
+        float* r = x + row * d;
+        float s = 0.f;
+        if (vec_ok) {
+            const float4* r4 = reinterpret_cast<const float4*>(r);
+            for (int64_t c = lane; c < d / 4; c += 32) {
+                float4 v = r4[c];
+                s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+            }
+        } else {
+            for (int64_t c = lane; c < d; c += 32) s = fmaf(r[c], r[c], s);
+        }
+        s = warp_sum(s);
+        if (s > 0.f) {
+            const float inv = 1.0f / sqrtf(s);
+            if (vec_ok) {
+                float4* r4 = reinterpret_cast<float4*>(r);
+                for (int64_t c = lane; c < d / 4; c += 32) {
+                    float4 v = r4[c];
+                    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+                    r4[c] = v;
+                }
+            } else {
+                for (int64_t c = lane; c < d; c += 32) r[c] *= inv;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// One warp per row.  Writes the zero-padded fp32 master row (optional), the bf16 shadow row,
+// |y|^2 and folds max|y|^2, max|y - bf16(y)|^2 into *stats (optional).
+__global__ void __launch_bounds__(kBlock) ingest_rows_kernel(const float* __restrict__ src, int64_t n, int d,
+                                                              int dp, float* __restrict__ dst_f32,
+                                                              __nv_bfloat16* __restrict__ dst_bf16,
+                                                              float* __restrict__ norms2,
+                                                              float* __restrict__ dnorms2, DbStats* stats,
+                                                              int vec_ok, int bf16_is_master) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = int64_t(gridDim.x) * kWarpsPerBlock;
+    float wmax_n = 0.f, wmax_d = 0.f;
+    for (int64_t row = int64_t(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5); row < n; row += warps) {
+        const float* r = src + row * int64_t(d);
+        float s = 0.f, e = 0.f;
+        for (int c = lane; c < dp / 4; c += 32) {
+            float4 v;
+            const int c0 = c * 4;
+            if (vec_ok && c0 + 3 < d) {
+                v = reinterpret_cast<const float4*>(r)[c];
+            } else {
+                v.x = c0 + 0 < d ? r[c0 + 0] : 0.f;
+                v.y = c0 + 1 < d ? r[c0 + 1] : 0.f;
+                v.z = c0 + 2 < d ? r[c0 + 2] : 0.f;
+                v.w = c0 + 3 < d ? r[c0 + 3] : 0.f;
+            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+            float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
+            if (bf16_is_master) v = make_float4(flo.x, flo.y, fhi.x, fhi.y);  // the rounded values ARE the row
+            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+            float dx = v.x - flo.x, dy = v.y - flo.y, dz = v.z - fhi.x, dw = v.w - fhi.y;
+            e = fmaf(dx, dx, e); e = fmaf(dy, dy, e); e = fmaf(dz, dz, e); e = fmaf(dw, dw, e);
+            if (dst_f32) reinterpret_cast<float4*>(dst_f32 + row * int64_t(dp))[c] = v;
+            uint2 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<uint32_t*>(&hi);
+            if (dst_bf16) reinterpret_cast<uint2*>(dst_bf16 + row * int64_t(dp))[c] = packed;
+        }
+        s = warp_sum(s);
+        e = warp_sum(e);
+        if (lane == 0) {
+            if (norms2) norms2[row] = s;
+            if (dnorms2) dnorms2[row] = e;
+        }
+        // NaN/Inf rows must not poison the bound: they can never be a valid neighbour anyway.
+        if (s == s && s < FLT_MAX) wmax_n = fmaxf(wmax_n, s);
+        if (e == e && e < FLT_MAX) wmax_d = fmaxf(wmax_d, e);
+    }
+    if (stats && lane == 0) {
+        atomicMax(&stats->max_norm2, __float_as_uint(wmax_n));
+        atomicMax(&stats->max_dnorm2, __float_as_uint(wmax_d));
+    }
+}
+
+// eps[q]: bound on |approx score - exact score| for query q against ANY database row, where the
+// approx score is the bf16 x bf16 -> fp32 tensor-core inner product (DESIGN.md "error bound"):
+//   |<x^,y^> - <x,y>| <= |dx||y| + |x||dy| + |dx||dy|      (Cauchy-Schwarz, dx = x^ - x)
+// plus a slack of dp * 2^-22 * |x||y| for the fp32 accumulation inside the MMA and the rerank.
+__global__ void query_eps_kernel(const float* __restrict__ xnorm2, const float* dnorm2, int64_t nq, int dp,
+                                 const DbStats* __restrict__ stats, int metric, float* eps) {  // dnorm2 may alias eps
+    int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float ymax = sqrtf(__uint_as_float(stats->max_norm2));
+    const float dymax = sqrtf(__uint_as_float(stats->max_dnorm2));
+    const float xn = sqrtf(xnorm2[q]);
+    const float dx = sqrtf(dnorm2[q]);
+    float e = dx * ymax + xn * dymax + dx * dymax + float(dp) * 2.384185791015625e-07f * xn * ymax;
+    e *= 1.001f;
+    if (metric == KNN_METRIC_L2) e *= 2.f;  // approx score is 2<x,y> - |y|^2
+    if (!(e == e) || e > FLT_MAX) e = FLT_MAX;
+    eps[q] = e;
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact fp32 scan.  Per (row, query) pair: lane l accumulates elements 4c..4c+3 for
+// c = l, l+32, ... in order with FMAs, then a butterfly sum - the rerank kernel repeats exactly
+// this order, so a pair gets the same bits whichever path scored it.
+template <int QT, int R, bool BF16DB>
+__global__ void __launch_bounds__(kBlock)
+scan_f32_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, int64_t nq, int dp,
+                const void* __restrict__ xb, const float* __restrict__ ynorm2, int64_t j0, int64_t j1, int metric,
+                float* __restrict__ out, int64_t ld_out) {
+    extern __shared__ float4 sq[];  // [QT][dp/4]
+    const int dp4 = dp / 4;
+    const int64_t q0 = int64_t(blockIdx.y) * QT;
+    const int nqt = int((nq - q0) < QT ? (nq - q0) : QT);
+    for (int i = threadIdx.x; i < QT * dp4; i += blockDim.x) {
+        const int t = i / dp4, c = i - t * dp4;
+        sq[i] = t < nqt ? reinterpret_cast<const float4*>(xq + (q0 + t) * int64_t(dp))[c]
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = int64_t(gridDim.x) * kWarpsPerBlock;
+    const int64_t wid = int64_t(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    for (int64_t base = j0 + wid * R; base < j1; base += warps * R) {
+        float acc[R][QT];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int t = 0; t < QT; ++t) acc[r][t] = 0.f;
+        for (int c = lane; c < dp4; c += 32) {
+            float4 y[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t row = base + r;
+                if (row < j1) {
+                    if (BF16DB) {
+                        uint2 p = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xb) +
+                                                                 row * int64_t(dp))[c];
+                        float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.x));
+                        float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.y));
+                        y[r] = make_float4(a.x, a.y, b.x, b.y);
+                    } else {
+                        y[r] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xb) +
+                                                                     row * int64_t(dp)) + c);
+                    }
+                } else {
+                    y[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < QT; ++t) {
+                const float4 q = sq[t * dp4 + c];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float a = acc[r][t];
+                    a = fmaf(y[r].x, q.x, a); a = fmaf(y[r].y, q.y, a);
+                    a = fmaf(y[r].z, q.z, a); a = fmaf(y[r].w, q.w, a);
+                    acc[r][t] = a;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = base + r;
+            float mine = 0.f;
+#pragma unroll
+            for (int t = 0; t < QT; ++t) {
+                const float v = warp_sum(acc[r][t]);
+                if (lane == t) mine = v;
+            }
+            if (row < j1 && lane < nqt) {
+                float v = mine;
+                if (metric == KNN_METRIC_L2) {
+                    v = xnorm2[q0 + lane] + ynorm2[row] - 2.0f * v;
+                    v = v < 0.f ? 0.f : v;
+                }
+                out[(q0 + lane) * ld_out + (row - j0)] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+template <bool BF16DB>
+__global__ void __launch_bounds__(kBlock)
+rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, int dp, const void* __restrict__ xb,
+              const float* __restrict__ ynorm2, int metric, float* __restrict__ cand_scores,
+              uint32_t* __restrict__ cand_ids, const int* __restrict__ counts, const float* __restrict__ tau,
+              int cap) {
+    extern __shared__ float4 sq[];  // [dp/4]
+    const int64_t q = blockIdx.x;
+    const int dp4 = dp / 4;
+    for (int i = threadIdx.x; i < dp4; i += blockDim.x)
+        sq[i] = reinterpret_cast<const float4*>(xq + q * int64_t(dp))[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int cnt = counts[q];
+    cnt = cnt < cap ? cnt : cap;
+    const float t = tau[q];
+    float* cs = cand_scores + q * int64_t(cap);
+    uint32_t* ci = cand_ids + q * int64_t(cap);
+    for (int i = warp; i < cnt; i += kWarpsPerBlock) {
+        const float approx = cs[i];
+        const uint32_t id = ci[i];
+        if (!(approx >= t) || id == kInvalidId) {  // warp-uniform
+            if (lane == 0) ci[i] = kInvalidId;
+            continue;
+        }
+        float a = 0.f;
+        for (int c = lane; c < dp4; c += 32) {
+            float4 y;
+            if (BF16DB) {
+                uint2 p = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xb) + int64_t(id) * dp)[c];
+                float2 u = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.x));
+                float2 v = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.y));
+                y = make_float4(u.x, u.y, v.x, v.y);
+            } else {
+                y = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xb) + int64_t(id) * dp) + c);
+            }
+            const float4 qv = sq[c];
+            a = fmaf(y.x, qv.x, a); a = fmaf(y.y, qv.y, a); a = fmaf(y.z, qv.z, a); a = fmaf(y.w, qv.w, a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) {
+            float v = a;
+            if (metric == KNN_METRIC_L2) {
+                v = xnorm2[q] + ynorm2[id] - 2.0f * v;
+                v = v < 0.f ? 0.f : v;
+            }
+            cs[i] = v;
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+int launch_normalize_l2(float* x, int64_t n, int64_t d, cudaStream_t s) {
+    if (n <= 0 || d <= 0) return KNN_OK;
+    const int vec_ok = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+    normalize_l2_kernel<<<grid_for_rows(n, kWarpsPerBlock, 8), kBlock, 0, s>>>(x, n, d, vec_ok);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_ingest(const float* src, int64_t n, int d, int dp, float* dst_f32, __nv_bfloat16* dst_bf16,
+                  float* norms2, DbStats* stats, cudaStream_t s) {
+    if (n <= 0) return KNN_OK;
+    const int vec_ok = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
+    ingest_rows_kernel<<<grid_for_rows(n, kWarpsPerBlock, 8), kBlock, 0, s>>>(src, n, d, dp, dst_f32, dst_bf16,
+                                                                               norms2, nullptr, stats, vec_ok, dst_f32 == nullptr);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_prep_queries(const float* xq, int64_t nq, int64_t nq_pad, int d, int dp, float* xq_f32,
+                        __nv_bfloat16* xq_bf16, float* xnorm2, float* eps, const DbStats* stats, int metric,
+                        cudaStream_t s) {
+    if (nq <= 0) return KNN_OK;
+    // eps doubles as scratch for |dx|^2 until query_eps_kernel overwrites it
+    const int vec_ok = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(xq) % 16 == 0);
+    ingest_rows_kernel<<<grid_for_rows(nq, kWarpsPerBlock, 8), kBlock, 0, s>>>(xq, nq, d, dp, xq_f32, xq_bf16,
+                                                                                xnorm2, eps, nullptr, vec_ok, 0);
+    KNN_CHECK_LAUNCH();
+    if (xq_bf16 && nq_pad > nq) {
+        KNN_CHECK_CUDA(cudaMemsetAsync(xq_bf16 + nq * int64_t(dp), 0, size_t(nq_pad - nq) * dp * sizeof(__nv_bfloat16), s));
+    }
+    query_eps_kernel<<<int((nq + 255) / 256), 256, 0, s>>>(xnorm2, eps, nq, dp, stats, metric, eps);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+template <int QT, bool BF16DB>
+static int launch_scan_t(const float* xq_f32, const float* xnorm2, int64_t nq, int dp, const void* xb,
+                         const float* ynorm2, int64_t j0, int64_t j1, int metric, float* out, int64_t ld_out,
+                         cudaStream_t s) {
+    constexpr int R = 4;
+    auto kern = scan_f32_kernel<QT, R, BF16DB>;
+    const size_t smem = size_t(QT) * dp * sizeof(float);
+    KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int64_t groups = (nq + QT - 1) / QT;
+    // split so that (x blocks) * (query groups) covers the SMs a few times over
+    int bx = grid_for_rows(j1 - j0, kWarpsPerBlock * R, 4);
+    for (int64_t g0 = 0; g0 < groups; g0 += 32768) {
+        const int64_t gn = groups - g0 < 32768 ? groups - g0 : 32768;
+        dim3 grid(bx, unsigned(gn));
+        kern<<<grid, kBlock, smem, s>>>(xq_f32 + g0 * QT * int64_t(dp), xnorm2 + g0 * QT, nq - g0 * QT, dp, xb,
+                                        ynorm2, j0, j1, metric, out + g0 * QT * ld_out, ld_out);
+        KNN_CHECK_LAUNCH();
+    }
+    return KNN_OK;
+}
+
+int launch_scan_f32(const float* xq_f32, const float* xnorm2, int64_t nq, int dp, const float* xb_f32,
+                    const __nv_bfloat16* xb_bf16, const float* ynorm2, int64_t j0, int64_t j1, int metric,
+                    float* out, int64_t ld_out, cudaStream_t s) {
+    if (nq <= 0 || j1 <= j0) return KNN_OK;
+    // QT queries stay in shared memory (QT * dp * 4 bytes): 8 for dp <= 6144, fewer beyond.
+    const bool bf = xb_f32 == nullptr;
+    const void* xb = bf ? static_cast<const void*>(xb_bf16) : static_cast<const void*>(xb_f32);
+    const size_t per_q = size_t(dp) * sizeof(float);
+    int qt = 8;
+    while (qt > 1 && per_q * qt > 200 * 1024) qt >>= 1;
+    if (per_q * qt > 200 * 1024) {
+        set_error("dimension %d too large for the scan kernel", dp);
+        return KNN_ERR_LIMIT;
+    }
+#define KNN_SCAN_CASE(QT)                                                                                   \
+    case QT:                                                                                                \
+        return bf ? launch_scan_t<QT, true>(xq_f32, xnorm2, nq, dp, xb, ynorm2, j0, j1, metric, out, ld_out, s) \
+                  : launch_scan_t<QT, false>(xq_f32, xnorm2, nq, dp, xb, ynorm2, j0, j1, metric, out, ld_out, s);
+    switch (qt) {
+        KNN_SCAN_CASE(8)
+        KNN_SCAN_CASE(4)
+        KNN_SCAN_CASE(2)
+        KNN_SCAN_CASE(1)
+    }
+#undef KNN_SCAN_CASE
+    return KNN_ERR_INVALID;
+}
+
+int launch_rerank(const float* xq_f32, const float* xnorm2, int64_t nq, int dp, const float* xb_f32,
+                  const __nv_bfloat16* xb_bf16, const float* ynorm2, int metric, float* cand_scores,
+                  uint32_t* cand_ids, const int* counts, const float* tau, int cap, cudaStream_t s) {
+    if (nq <= 0) return KNN_OK;
+    const size_t smem = size_t(dp) * sizeof(float);
+    if (xb_f32) {
+        auto kern = rerank_kernel<false>;
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<unsigned(nq), kBlock, smem, s>>>(xq_f32, xnorm2, dp, xb_f32, ynorm2, metric, cand_scores, cand_ids,
+                                                counts, tau, cap);
+    } else {
+        auto kern = rerank_kernel<true>;
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<unsigned(nq), kBlock, smem, s>>>(xq_f32, xnorm2, dp, xb_bf16, ynorm2, metric, cand_scores, cand_ids,
+                                                counts, tau, cap);
+    }
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+}  // namespace knn

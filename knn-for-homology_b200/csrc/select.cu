@@ -1,0 +1,398 @@
+// Top-k selection kernels: radix narrowing on composite (score, id) keys followed by a
+// shared-memory bitonic sort of the few survivors.  One CTA per (query, segment).
+//
+// Replaces the per-query heap / reservoir of faiss's result handlers (upstream faiss
+// utils/Heap.h, ResultHandler.h - third-party, see oracle/flat_oracle.py) behind
+// index.search (cath/search.py:24, pfam/proteins_search.py:49, seqvec_search/main.py:45):
+// best first, equal scores -> lower id first, label -1 / +-FLT_MAX padding.
+#include "common.cuh"
+
+namespace knn {
+namespace {
+
+struct SelectSmem {
+    uint64_t keys[kSortCap];
+    int hist[256];
+    uint64_t red_a[32];
+    uint64_t red_b[32];
+    int scount;
+    int bucket;
+    int cum_gt;
+    int bucket_count;
+};
+
+// Narrow [prefix, mask] one 8-bit digit at a time (most significant differing bit first) until
+// the boundary bucket plus everything strictly above it fits in `stop` elements, or all bits are
+// fixed.  On return every key with (key & mask) > prefix is among the `k` best, `need` more have
+// to come out of the bucket (key & mask) == prefix, which holds `bucket_count` keys.
+template <typename Key, class Gen>
+__device__ void radix_narrow(const Gen& gen, int L, int k, int stop, Key mn, Key mx, int* hist, int* sh_bucket,
+                             int* sh_cum, int* sh_cnt, Key& prefix, Key& mask, int& need, int& bucket_count) {
+    constexpr int kBits = int(sizeof(Key)) * 8;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const Key diff = mn ^ mx;
+    const int hi_bit = kBits - 1 - (sizeof(Key) == 8 ? __clzll((long long)diff) : __clz((int)diff));
+    int shift = hi_bit >= 7 ? hi_bit - 7 : 0;
+    mask = hi_bit == kBits - 1 ? Key(0) : Key(~Key(0)) << (hi_bit + 1);
+    prefix = mx & mask;
+    need = k;
+    for (;;) {
+        for (int i = tid; i < 256; i += T) hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < L; i += T) {
+            const Key key = gen(i);
+            if ((key & mask) == prefix) atomicAdd(&hist[int((key >> shift) & Key(0xFF))], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int loc[8];
+            int s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                loc[j] = hist[8 * tid + j];
+                s += loc[j];
+            }
+            int suf = s;  // inclusive suffix sum over lanes (bins of this lane and all higher lanes)
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, off);
+                if (tid + off < 32) suf += v;
+            }
+            const int above = suf - s;
+            if (above < need && need <= above + s) {  // exactly one lane owns the boundary bucket
+                int cum = above;
+#pragma unroll
+                for (int j = 7; j >= 0; --j) {
+                    if (cum + loc[j] >= need) {
+                        *sh_bucket = 8 * tid + j;
+                        *sh_cum = cum;
+                        *sh_cnt = loc[j];
+                        break;
+                    }
+                    cum += loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        const int b = *sh_bucket;
+        need -= *sh_cum;
+        bucket_count = *sh_cnt;
+        prefix |= Key(b) << shift;
+        mask |= Key(0xFF) << shift;
+        if ((k - need) + bucket_count <= stop || shift == 0) break;
+        shift = shift >= 8 ? shift - 8 : 0;
+    }
+}
+
+template <typename Key>
+__device__ void block_minmax(Key mn, Key mx, Key* red_a, Key* red_b, Key& out_mn, Key& out_mx) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const Key a = __shfl_xor_sync(0xffffffffu, mn, off);
+        const Key b = __shfl_xor_sync(0xffffffffu, mx, off);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) {
+        red_a[warp] = mn;
+        red_b[warp] = mx;
+    }
+    __syncthreads();
+    mn = red_a[0];
+    mx = red_b[0];
+    for (int w = 1; w < nw; ++w) {
+        mn = red_a[w] < mn ? red_a[w] : mn;
+        mx = red_b[w] > mx ? red_b[w] : mx;
+    }
+    out_mn = mn;
+    out_mx = mx;
+    __syncthreads();
+}
+
+__device__ void bitonic_sort_desc(uint64_t* keys, int P) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (P >> 1); i += T) {
+                const int pos = 2 * i - (i & (stride - 1));
+                const int j = pos + stride;
+                const uint64_t a = keys[pos], b = keys[j];
+                const bool desc = (pos & size) == 0;
+                if ((a < b) == desc) {
+                    keys[pos] = b;
+                    keys[j] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Leaves the best min(k, L) keys of gen(0..L) sorted (descending) in sm.keys[0..) and returns
+// their number.  Requires k <= kSortCap / 2.  Keys equal to 0 are padding and sort last.
+template <class Gen>
+__device__ int block_select_sorted(const Gen& gen, int L, int k, SelectSmem& sm) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    int n;
+    if (L <= kSortCap) {
+        for (int i = tid; i < L; i += T) sm.keys[i] = gen(i);
+        n = L;
+    } else {
+        uint64_t mn = ~0ull, mx = 0ull;
+        for (int i = tid; i < L; i += T) {
+            const uint64_t key = gen(i);
+            mn = key < mn ? key : mn;
+            mx = key > mx ? key : mx;
+        }
+        block_minmax<uint64_t>(mn, mx, sm.red_a, sm.red_b, mn, mx);
+        if (mn == mx) {  // only possible when every key is padding
+            n = k < L ? k : L;
+            for (int i = tid; i < n; i += T) sm.keys[i] = mx;
+        } else {
+            uint64_t prefix, mask;
+            int need, bucket_count;
+            radix_narrow<uint64_t>(gen, L, k, kSortCap, mn, mx, sm.hist, &sm.bucket, &sm.cum_gt, &sm.bucket_count,
+                                   prefix, mask, need, bucket_count);
+            if (tid == 0) sm.scount = 0;
+            __syncthreads();
+            for (int i = tid; i < L; i += T) {
+                const uint64_t key = gen(i);
+                if ((key & mask) >= prefix) {
+                    const int p = atomicAdd(&sm.scount, 1);
+                    if (p < kSortCap) sm.keys[p] = key;  // overflow only for a bucket of identical padding keys
+                }
+            }
+            __syncthreads();
+            n = sm.scount < kSortCap ? sm.scount : kSortCap;
+        }
+    }
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int i = n + tid; i < P; i += T) sm.keys[i] = 0ull;
+    bitonic_sort_desc(sm.keys, P);
+    return n < k ? n : k;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelectThreads)
+select_dense_kernel(const float* __restrict__ scores, int64_t ld, int64_t ncols, int seg_len, uint32_t id_base, int k,
+                    int largest, float* __restrict__ list_scores, uint32_t* __restrict__ list_ids, int64_t list_ld,
+                    int64_t list_off) {
+    __shared__ SelectSmem sm;
+    const int64_t q = blockIdx.y;
+    const int64_t seg = blockIdx.x;
+    const int64_t c0 = seg * seg_len;
+    const int L = int((ncols - c0) < seg_len ? (ncols - c0) : seg_len);
+    const float* row = scores + q * ld + c0;
+    const uint32_t base = id_base + uint32_t(c0);
+    auto gen = [=] __device__(int i) { return make_key(row[i], base + uint32_t(i), largest); };
+    const int n = block_select_sorted(gen, L, k, sm);
+    float* os = list_scores + q * list_ld + list_off + seg * k;
+    uint32_t* oi = list_ids + q * list_ld + list_off + seg * k;
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+        const uint64_t key = r < n ? sm.keys[r] : 0ull;
+        os[r] = key ? key_score(key, largest) : 0.f;
+        oi[r] = key ? key_id(key) : kInvalidId;
+    }
+}
+
+__device__ __forceinline__ void write_final(const SelectSmem& sm, int n, int k, int largest, float* D, int64_t* I,
+                                            int64_t id_base) {
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+        const uint64_t key = r < n ? sm.keys[r] : 0ull;
+        if (key) {
+            D[r] = key_score(key, largest);
+            I[r] = int64_t(key_id(key)) + id_base;
+        } else {  // heap neutral element of faiss: label -1
+            D[r] = largest ? -FLT_MAX : FLT_MAX;
+            I[r] = -1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+select_final_kernel(const float* __restrict__ list_scores, const uint32_t* __restrict__ list_ids,
+                    const int* __restrict__ counts, int64_t list_ld, int64_t fixed_len, int k, int largest,
+                    float* __restrict__ D, int64_t* __restrict__ I, int64_t id_base) {
+    __shared__ SelectSmem sm;
+    const int64_t q = blockIdx.x;
+    int64_t len = fixed_len;
+    if (counts) len = counts[q] < list_ld ? counts[q] : list_ld;
+    const float* ls = list_scores + q * list_ld;
+    const uint32_t* li = list_ids + q * list_ld;
+    auto gen = [=] __device__(int i) { return make_key(ls[i], li[i], largest); };
+    const int n = block_select_sorted(gen, int(len), k, sm);
+    write_final(sm, n, k, largest, D + q * k, I + q * k, id_base);
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+merge_lists_kernel(const float* __restrict__ D_lists, const int64_t* __restrict__ I_lists, int nlists, int64_t nq,
+                   int k, int largest, float* __restrict__ D, int64_t* __restrict__ I) {
+    __shared__ SelectSmem sm;
+    const int64_t q = blockIdx.x;
+    auto gen = [=] __device__(int i) {
+        const int l = i / k, r = i - l * k;
+        const int64_t off = (int64_t(l) * nq + q) * k + r;
+        const int64_t id = I_lists[off];
+        return make_key(D_lists[off], id < 0 ? kInvalidId : uint32_t(id), largest);
+    };
+    const int n = block_select_sorted(gen, nlists * k, k, sm);
+    write_final(sm, n, k, largest, D + q * k, I + q * k, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// Tighten: per query, k-th best approximate score so far -> new candidate threshold, then drop
+// the candidates that fell below it (order-preserving in-place compaction).
+struct TightenSmem {
+    int hist[256];
+    uint32_t red_a[32];
+    uint32_t red_b[32];
+    int bucket;
+    int cum_gt;
+    int bucket_count;
+    int warp_tot[32];
+    int base;
+};
+
+__global__ void __launch_bounds__(256)
+tighten_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __restrict__ cand_scores,
+               uint32_t* __restrict__ cand_ids, int cap, const float* __restrict__ eps, int k, int compact,
+               int* __restrict__ overflow) {
+    __shared__ TightenSmem sm;
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, T = blockDim.x;
+    int cnt = counts[q];
+    if (cnt > cap) {
+        if (tid == 0) atomicExch(overflow, 1);
+        cnt = cap;
+    }
+    if (cnt < k || cnt == 0) return;  // fewer than k candidates seen: everything stays a candidate
+    float* cs = cand_scores + q * int64_t(cap);
+    uint32_t* ci = cand_ids + q * int64_t(cap);
+    auto gen = [=] __device__(int i) {
+        const float s = cs[i];
+        return s != s ? 0u : orderable_f32(s);
+    };
+    uint32_t mn = ~0u, mx = 0u;
+    for (int i = tid; i < cnt; i += T) {
+        const uint32_t key = gen(i);
+        mn = key < mn ? key : mn;
+        mx = key > mx ? key : mx;
+    }
+    block_minmax<uint32_t>(mn, mx, sm.red_a, sm.red_b, mn, mx);
+    uint32_t kth = mx;
+    if (mn != mx) {
+        uint32_t prefix, mask;
+        int need, bucket_count;
+        radix_narrow<uint32_t>(gen, cnt, k, 0, mn, mx, sm.hist, &sm.bucket, &sm.cum_gt, &sm.bucket_count, prefix, mask,
+                               need, bucket_count);
+        kth = prefix;  // all bits fixed: the k-th largest key itself
+    }
+    const float kth_score = from_orderable_f32(kth);
+    const float e = eps[q];
+    float t = kth_score - 2.0f * e;
+    if (!(t == t)) t = -FLT_MAX;
+    // the bound only ever rises (k-th best over a superset); keep the max for safety with NaNs
+    const float old = thr[q];
+    if (old > t) t = old;
+    __syncthreads();
+    if (tid == 0) thr[q] = t;
+    if (!compact) return;
+    // ordered compaction, chunk by chunk: writes land at or before the positions already read
+    if (tid == 0) sm.base = 0;
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+    for (int c0 = 0; c0 < cnt; c0 += T) {
+        const int i = c0 + tid;
+        float s = 0.f;
+        uint32_t id = kInvalidId;
+        bool keep = false;
+        if (i < cnt) {
+            s = cs[i];
+            id = ci[i];
+            keep = (s >= t) && id != kInvalidId;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        const int wpre = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) sm.warp_tot[warp] = __popc(ballot);
+        __syncthreads();  // all reads of this chunk done, warp totals visible
+        int off = sm.base;
+        for (int w = 0; w < warp; ++w) off += sm.warp_tot[w];
+        if (keep) {
+            cs[off + wpre] = s;
+            ci[off + wpre] = id;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < nw; ++w) tot += sm.warp_tot[w];
+            sm.base += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) counts[q] = sm.base;
+}
+
+__global__ void init_filter_kernel(float* thr, int* counts, int64_t nq, int64_t nq_pad, int first_count) {
+    const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nq_pad) return;
+    thr[q] = q < nq ? -FLT_MAX : FLT_MAX;
+    counts[q] = q < nq ? first_count : 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+int launch_select_dense(const float* scores, int64_t ld, int64_t ncols, int64_t nq, int seg_len, uint32_t id_base,
+                        int k, int largest, float* list_scores, uint32_t* list_ids, int64_t list_ld,
+                        int64_t list_off, cudaStream_t s) {
+    if (nq <= 0 || ncols <= 0) return KNN_OK;
+    const int64_t nseg = (ncols + seg_len - 1) / seg_len;
+    for (int64_t q0 = 0; q0 < nq; q0 += 65535) {
+        const int64_t qn = nq - q0 < 65535 ? nq - q0 : 65535;
+        dim3 grid((unsigned)nseg, (unsigned)qn, 1u);
+        select_dense_kernel<<<grid, kSelectThreads, 0, s>>>(scores + q0 * ld, ld, ncols, seg_len, id_base, k, largest,
+                                                            list_scores + q0 * list_ld, list_ids + q0 * list_ld,
+                                                            list_ld, list_off);
+        KNN_CHECK_LAUNCH();
+    }
+    return KNN_OK;
+}
+
+int launch_select_final(const float* list_scores, const uint32_t* list_ids, const int* counts, int64_t list_ld,
+                        int64_t fixed_len, int64_t nq, int k, int largest, float* D, int64_t* I, int64_t id_base,
+                        cudaStream_t s) {
+    if (nq <= 0) return KNN_OK;
+    select_final_kernel<<<unsigned(nq), kSelectThreads, 0, s>>>(list_scores, list_ids, counts, list_ld, fixed_len, k,
+                                                                largest, D, I, id_base);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_merge_lists(const float* D_lists, const int64_t* I_lists, int nlists, int64_t nq, int k, int largest,
+                       float* D, int64_t* I, cudaStream_t s) {
+    if (nq <= 0) return KNN_OK;
+    merge_lists_kernel<<<unsigned(nq), kSelectThreads, 0, s>>>(D_lists, I_lists, nlists, nq, k, largest, D, I);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int compact, float* tau_out, int* overflow,
+                   cudaStream_t s) {
+    (void)tau_out;
+    if (nq <= 0) return KNN_OK;
+    tighten_kernel<<<unsigned(nq), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap, eps, k,
+                                                compact, overflow);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_init_filter(FilterState st, int64_t nq, int64_t nq_pad, int first_count, cudaStream_t s) {
+    init_filter_kernel<<<unsigned((nq_pad + 255) / 256), 256, 0, s>>>(st.thr, st.counts, nq, nq_pad, first_count);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+}  // namespace knn

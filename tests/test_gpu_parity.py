@@ -1,0 +1,392 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI
+(ctypes -> libknn_b200.so), against the CPU oracle on the same seeded inputs, against the
+committed golden vectors of the reference's own tests, and through size-independent
+properties at larger sizes.  Bar: ids identical except fp64-arbitrated near-ties
+(oracle/parity.py), distances within 1e-5 relative."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import flat_oracle as fo
+from oracle.evaluate import Fixture, evaluate_ids
+from oracle.parity import check_parity
+
+pytestmark = pytest.mark.gpu
+
+IP, L2 = 0, 1
+
+
+@pytest.fixture(scope="module")
+def knn():
+    import knn_b200
+
+    assert knn_b200._lib.load().knn_device_count() >= 1, "no CUDA device: the CUDA path cannot run"
+    return knn_b200
+
+
+def _data(nq, nb, d, seed, normalize=True, scale=1.0):
+    rng = np.random.default_rng(seed)
+    xb = (rng.standard_normal((nb, d)) * scale).astype(np.float32)
+    xq = (rng.standard_normal((nq, d)) * scale).astype(np.float32)
+    if normalize:
+        fo.normalize_L2(xb)
+        fo.normalize_L2(xq)
+    return xq, xb
+
+
+def _search(knn, xq, xb, k, metric, path=0, **params):
+    idx = knn.IndexFlat(xb.shape[1], metric)
+    idx.set_param("path", path)
+    for name, v in params.items():
+        idx.set_param(name, v)
+    idx.train(xb)
+    idx.add(xb)
+    assert idx.ntotal == xb.shape[0]
+    D, I = idx.search(xq, k)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (xq.shape[0], k) == I.shape
+    assert D.flags.c_contiguous and I.flags.c_contiguous
+    return D, I, idx
+
+
+# ---------------------------------------------------------------------------------------------
+def test_normalize_l2_matches_oracle(knn):
+    rng = np.random.default_rng(1)
+    for shape in [(17, 1024), (5, 33), (1000, 128), (3, 7)]:
+        x = (rng.standard_normal(shape) * 3).astype(np.float32)
+        x[1] = 0
+        ref = x.copy()
+        fo.normalize_L2(ref)
+        got = x.copy()
+        assert knn.normalize_L2(got) is None  # in place, like faiss
+        np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-7)
+        assert np.array_equal(got[1], np.zeros(shape[1], np.float32))
+    with pytest.raises(TypeError):
+        knn.normalize_L2(x.astype(np.float64))
+    with pytest.raises(ValueError):
+        knn.normalize_L2(np.asfortranarray(x))
+
+
+def _faiss_search_flow(knn, fx_dir, k, path=0):
+    """seqvec_search/main.py:29-50 restated on top of the shim."""
+    queries = np.load(fx_dir / "test.npy")
+    haystack = np.load(fx_dir / "train.npy")
+    knn.normalize_L2(queries)
+    knn.normalize_L2(haystack)
+    index = knn.IndexFlat(haystack.shape[1], knn.METRIC_INNER_PRODUCT)
+    index.set_param("path", path)
+    index.train(haystack)
+    index.add(haystack)
+    scores, result = index.search(queries, k)
+    return result, scores
+
+
+def test_reference_known_answer_small_random(knn, golden_dir, expected):
+    """/root/reference/tests/test_main.py:10-18 through the CUDA path."""
+    I, D = _faiss_search_flow(knn, golden_dir / "small-random", 5)
+    auc1s, tps = evaluate_ids(Fixture(golden_dir / "small-random"), I)
+    assert auc1s == [1.0, 1 / 3, 2 / 3, 0.0, 0.0, 1 / 3]
+    assert tps == [1.0, 2 / 3, 2 / 3, 1.0, 1.0, 1.0]
+    assert np.array_equal(I, expected["small-random.ip.k5.I"])
+    np.testing.assert_allclose(D, expected["small-random.ip.k5.D"], rtol=1e-5)
+
+
+def test_reference_known_answer_pfam_20_10(knn, golden_dir, expected):
+    """/root/reference/tests/test_main.py:21-27 (kNN half) through the CUDA path."""
+    I, D = _faiss_search_flow(knn, golden_dir / "pfam-20-10", 10)
+    auc1s, tps = evaluate_ids(Fixture(golden_dir / "pfam-20-10"), I)
+    assert np.mean(auc1s) == 0.871
+    assert np.mean(tps) == 0.91
+    assert np.array_equal(I, expected["pfam-20-10.ip.k10.I"])
+    np.testing.assert_allclose(D, expected["pfam-20-10.ip.k10.D"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["pfam-20-10-sum", "pfam-20-dist"])
+def test_regression_fixtures(knn, golden_dir, expected, name):
+    summary = json.loads((golden_dir / "expected.json").read_text())
+    I, D = _faiss_search_flow(knn, golden_dir / name, 13)
+    auc1s, tps = evaluate_ids(Fixture(golden_dir / name), I)
+    assert np.mean(auc1s) == summary[name]["mean_auc1"]
+    assert np.mean(tps) == summary[name]["mean_tp"]
+    assert np.array_equal(I, expected[f"{name}.ip.k13.I"])
+    np.testing.assert_allclose(D, expected[f"{name}.ip.k13.D"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("mname,metric", [("ip", IP), ("l2", L2)])
+def test_cath_search_flow(knn, golden_dir, expected, mname, metric):
+    """cath/search.py:13-26 restated: all-vs-all with hits+1, both metrics, self hit dropped."""
+    emb = np.load(golden_dir / "pfam-20-10/train.npy")
+    x = emb
+    if metric == IP:
+        x = emb.copy()
+        knn.normalize_L2(x)
+    index = knn.IndexFlat(x.shape[1], metric)
+    index.add(x)
+    scores, results = index.search(x, 11)
+    I, D = results[:, 1:], scores[:, 1:]
+    assert np.array_equal(results[:, 0], np.arange(x.shape[0]))  # column 0 is the self hit
+    ref_x = emb.copy()
+    if metric == IP:
+        fo.normalize_L2(ref_x)
+    check_parity(np.ascontiguousarray(D), np.ascontiguousarray(I),
+                 expected[f"cath-search.pfam-20-10-train.{mname}.hits10.D"],
+                 expected[f"cath-search.pfam-20-10-train.{mname}.hits10.I"], ref_x, ref_x, metric, max_excused_frac=0.01)
+
+
+@pytest.mark.parametrize("mname,metric", [("ip", IP), ("l2", L2)])
+def test_k_larger_than_ntotal_pads(knn, golden_dir, expected, mname, metric):
+    xb = np.load(golden_dir / "small-random/train.npy")
+    xq = np.load(golden_dir / "small-random/test.npy")
+    D, I, _ = _search(knn, xq, xb, 16, metric)
+    assert np.array_equal(I, expected[f"small-random.raw.{mname}.k16.I"])
+    ref_D = expected[f"small-random.raw.{mname}.k16.D"]
+    assert np.array_equal(D[:, 11:], ref_D[:, 11:])  # -FLT_MAX / +FLT_MAX
+    np.testing.assert_allclose(D[:, :11], ref_D[:, :11], rtol=1e-5)
+
+
+def test_empty_cases(knn):
+    idx = knn.IndexFlat(16, IP)
+    D, I = idx.search(np.zeros((3, 16), np.float32), 4)  # empty index: all padding
+    assert (I == -1).all() and (D == -np.finfo(np.float32).max).all()
+    idx.add(np.ones((2, 16), np.float32))
+    D, I = idx.search(np.zeros((0, 16), np.float32), 4)  # no queries
+    assert D.shape == (0, 4) and I.shape == (0, 4)
+    with pytest.raises(AssertionError):
+        idx.add(np.ones((2, 17), np.float32))
+    with pytest.raises(ValueError):
+        idx.search(np.ones((2, 16), np.float32), 0)
+    with pytest.raises(Exception):
+        idx.search(np.ones((2, 16), np.float32), knn.MAX_K + 1)
+    with pytest.raises(NotImplementedError):
+        knn.IndexLSH(16, 8)
+
+
+# ---------------------------------------------------------------------------------------------
+EXACT_CASES = [
+    # nq, nb, d, k, normalize
+    (6, 11, 1024, 5, True),
+    (1, 1, 8, 1, False),
+    (37, 5000, 64, 10, True),
+    (9, 40000, 100, 100, True),     # d padded to 128, two select segments
+    (130, 3000, 1024, 1000, True),  # k close to a segment's sort capacity
+    (3, 70000, 32, 2048, False),    # k = KNN_MAX_K, radix path
+    (64, 4096, 1900, 13, True),     # UniRep-like width
+    (20, 9000, 20, 11, False),      # amino-acid-composition-like width
+]
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("case", EXACT_CASES)
+def test_exact_path_parity(knn, case, metric):
+    nq, nb, d, k, norm = case
+    xq, xb = _data(nq, nb, d, seed=nq + nb + d, normalize=norm and metric == IP, scale=2.5)
+    D, I, idx = _search(knn, xq, xb, k, metric, path=1)
+    assert idx.stat("path") == 1
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    stats = check_parity(D, I, D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-3)
+    assert stats["positions"] == nq * k
+
+
+TENSOR_CASES = [
+    # nq, nb, d, k, query_batch
+    (300, 20000, 1024, 100, 16384),
+    (128, 9000, 1024, 10, 16384),
+    (200, 16384, 64, 5, 128),        # several query batches, smallest K loop
+    (77, 12345, 96, 50, 16384),      # padded d, ragged everything
+    (150, 30000, 1024, 1000, 16384),
+    (64, 8192, 1280, 1, 16384),
+    (513, 50000, 512, 2048, 256),    # k = KNN_MAX_K: candidate capacity 16384
+]
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("case", TENSOR_CASES)
+def test_tensor_path_parity(knn, case, metric):
+    nq, nb, d, k, qb = case
+    xq, xb = _data(nq, nb, d, seed=7 * nq + nb, normalize=metric == IP, scale=1.7)
+    D, I, idx = _search(knn, xq, xb, k, metric, path=2, query_batch=qb)
+    assert idx.stat("path") == 2 and idx.stat("gemm_launches") >= 1
+    assert idx.stat("overflow_batches") == 0
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    check_parity(D, I, D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-3)
+    # the rerank repeats the scan kernel's arithmetic: both device paths agree bit for bit
+    D1, I1, _ = _search(knn, xq, xb, k, metric, path=1)
+    assert np.array_equal(I1, I)
+    assert np.array_equal(D1, D)
+
+
+def test_tensor_path_real_embeddings(knn, golden_dir):
+    """Real (clustered) SeqVec embeddings tiled into a larger database: stresses the candidate
+    margin where many scores sit close together."""
+    base = np.concatenate([np.load(golden_dir / n / f) for n in ["pfam-20-10", "pfam-20-10-sum", "pfam-20-dist"]
+                           for f in ["train.npy", "test.npy"]])
+    rng = np.random.default_rng(5)
+    xb = np.concatenate([base + rng.standard_normal(base.shape).astype(np.float32) * 0.02 * s for s in range(1, 9)])
+    xq = base[:400].copy()
+    fo.normalize_L2(xb)
+    fo.normalize_L2(xq)
+    D, I, idx = _search(knn, xq, xb, 100, IP, path=2)
+    assert idx.stat("path") == 2
+    D_ref, I_ref = fo.knn_flat(xq, xb, 100, IP)
+    check_parity(D, I, D_ref, I_ref, xq, xb, IP, max_excused_frac=5e-3)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_exact_ties_lower_id_first(knn, path):
+    """Duplicated database rows give exactly equal scores: the lower id must come first."""
+    xq, xb = _data(96, 4500, 128, seed=11)
+    xb = np.concatenate([xb, xb])  # row j and row j + 4500 are identical
+    D, I, _ = _search(knn, xq, xb, 20, IP, path=path, tensor_min_n=1)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 20, IP)
+    check_parity(D, I, D_ref, I_ref, xq, xb, IP, max_excused_frac=5e-3)
+    pairs = I.reshape(96, 10, 2)
+    assert (pairs[:, :, 1] == pairs[:, :, 0] + 4500).all()
+    assert np.array_equal(D[:, 0::2], D[:, 1::2])
+
+
+def test_candidate_overflow_falls_back_not_truncates(knn):
+    """Every database row identical -> every score ties -> the candidate lists overflow; the
+    engine must notice and still return the exact answer (ids 0..k-1)."""
+    nb, d, k = 40000, 64, 10
+    row = np.random.default_rng(2).standard_normal(d).astype(np.float32)
+    xb = np.tile(row, (nb, 1))
+    xq = np.tile(row, (128, 1))
+    D, I, idx = _search(knn, xq, xb, k, IP, path=2)
+    assert idx.stat("overflow_batches") >= 1
+    assert np.array_equal(I, np.tile(np.arange(k), (128, 1)))
+
+
+def test_incremental_add_and_reset(knn):
+    xq, xb = _data(40, 6000, 256, seed=3)
+    idx = knn.IndexFlat(256, IP)
+    idx.add(xb[:1000])
+    idx.add(xb[1000:1001])
+    idx.add(xb[1001:])
+    assert idx.ntotal == 6000
+    D, I = idx.search(xq, 7)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 7, IP)
+    check_parity(D, I, D_ref, I_ref, xq, xb, IP)
+    got = idx.reconstruct_n(998, 5)
+    assert np.array_equal(got, xb[998:1003])
+    idx.reset()
+    assert idx.ntotal == 0
+    idx.add(xb[:10])
+    D, I = idx.search(xq, 3)
+    assert I.max() < 10
+
+
+def test_add_copies_caller_memory(knn):
+    """faiss semantics: the drivers mutate their array after add (pfam/proteins_search.py:37,49)."""
+    xq, xb = _data(5, 100, 64, seed=9)
+    idx = knn.IndexFlat(64, IP)
+    keep = xb.copy()
+    idx.add(xb)
+    xb[:] = 0
+    D, I = idx.search(xq, 3)
+    D_ref, I_ref = fo.knn_flat(xq, keep, 3, IP)
+    check_parity(D, I, D_ref, I_ref, xq, keep, IP)
+
+
+def test_input_coercion_like_faiss(knn):
+    xq, xb = _data(5, 300, 48, seed=4)
+    idx = knn.IndexFlat(48, L2)
+    idx.add(xb.astype(np.float64))            # dtype coerced
+    D, I = idx.search(np.asfortranarray(xq), 4)  # layout coerced
+    D_ref, I_ref = fo.knn_flat(xq, xb, 4, L2)
+    check_parity(D, I, D_ref, I_ref, xq, xb, L2)
+    fp16 = xb.astype(np.float16)               # cath/search.py:40 up-casts fp16 files
+    idx2 = knn.IndexFlat(48, L2)
+    idx2.add(fp16.astype(np.float32))
+    D, I = idx2.search(xq, 4)
+    D_ref, I_ref = fo.knn_flat(xq, fp16.astype(np.float32), 4, L2)
+    check_parity(D, I, D_ref, I_ref, xq, fp16.astype(np.float32), L2)
+
+
+def test_write_read_index_roundtrip(knn, tmp_path):
+    xq, xb = _data(8, 777, 40, seed=6)
+    for metric, fourcc in [(IP, b"IxFI"), (L2, b"IxF2")]:
+        idx = knn.IndexFlat(40, metric)
+        idx.add(xb)
+        path = tmp_path / f"flat{metric}.index"
+        knn.write_index(idx, str(path))
+        raw = path.read_bytes()
+        assert raw[:4] == fourcc
+        assert len(raw) == 4 + 4 + 8 + 8 + 8 + 1 + 4 + 8 + xb.nbytes  # header + vectors, as faiss writes it
+        assert np.array_equal(np.frombuffer(raw[-xb.nbytes:], np.float32).reshape(xb.shape), xb)
+        back = knn.read_index(str(path))
+        assert (back.d, back.ntotal, back.metric_type) == (40, 777, metric)
+        D0, I0 = idx.search(xq, 5)
+        D1, I1 = back.search(xq, 5)
+        assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+
+
+def test_bf16_storage_index(knn):
+    """Config C5: the bf16 values ARE the database; results must equal an fp32 search over the
+    bf16-rounded rows."""
+    import torch
+
+    xq, xb = _data(200, 20000, 256, seed=8)
+    xb_r = torch.from_numpy(xb).to(torch.bfloat16).to(torch.float32).numpy()
+    for path in (1, 2):
+        idx = knn.IndexFlat(256, IP, bf16_storage=True)
+        idx.set_param("path", path)
+        idx.add(xb)
+        D, I = idx.search(xq, 50)
+        D_ref, I_ref = fo.knn_flat(xq, xb_r, 50, IP)
+        check_parity(D, I, D_ref, I_ref, xq, xb_r, IP, max_excused_frac=2e-3)
+
+
+def test_torch_device_api_and_merge(knn):
+    import torch
+
+    xq, xb = _data(256, 24000, 128, seed=12)
+    dev = torch.device("cuda:0")
+    tq, tb = torch.from_numpy(xq).to(dev), torch.from_numpy(xb).to(dev)
+    full = knn.IndexFlat(128, IP)
+    full.add(tb)
+    D, I = full.search(tq, 30)
+    assert D.is_cuda and I.dtype == torch.int64
+    D_ref, I_ref = fo.knn_flat(xq, xb, 30, IP)
+    check_parity(D.cpu().numpy(), I.cpu().numpy(), D_ref, I_ref, xq, xb, IP, max_excused_frac=2e-3)
+    # row-sharded: 3 ragged shards, global ids via id_base, merged on the device
+    bounds = [0, 7000, 15001, 24000]
+    Ds, Is = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        shard = knn.IndexFlat(128, IP)
+        shard.add(tb[a:b])
+        d_, i_ = shard.search(tq, 30, id_base=a)
+        Ds.append(d_)
+        Is.append(i_)
+    Dm, Im = knn.merge_topk(torch.stack(Ds), torch.stack(Is), IP)
+    assert torch.equal(Im, I) and torch.equal(Dm, D)
+    # device normalize
+    t = torch.randn(100, 64, device=dev)
+    ref = t.cpu().numpy().copy()
+    fo.normalize_L2(ref)
+    knn.normalize_L2(t)
+    np.testing.assert_allclose(t.cpu().numpy(), ref, rtol=2e-6, atol=1e-7)
+
+
+def test_properties_at_scale(knn):
+    """All-vs-all on 60k x 1024 normalised rows, k=100, tensor path: properties that need no
+    oracle (sorted, self hit first with score ~1, ids unique and in range), plus an exhaustive
+    oracle check on a sample of the queries."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    xb = torch.randn(60000, 1024, device="cuda", generator=g)
+    knn.normalize_L2(xb)
+    idx = knn.IndexFlat(1024, IP)
+    idx.add(xb)
+    D, I = idx.search(xb[:8192], 100)
+    assert idx.stat("path") == 2 and idx.stat("overflow_batches") == 0
+    Dn, In = D.cpu().numpy(), I.cpu().numpy()
+    assert (np.diff(Dn, axis=1) <= 0).all()
+    assert np.array_equal(In[:, 0], np.arange(8192))
+    np.testing.assert_allclose(Dn[:, 0], 1.0, atol=1e-5)
+    assert In.min() >= 0 and In.max() < 60000
+    assert all(len(set(r)) == 100 for r in In[::64].tolist())
+    sample = np.arange(0, 8192, 128)
+    xb_h = xb.cpu().numpy()
+    D_ref, I_ref = fo.knn_flat(xb_h[sample], xb_h, 100, IP)
+    check_parity(Dn[sample], In[sample], D_ref, I_ref, xb_h[sample], xb_h, IP, max_excused_frac=5e-3)
