@@ -208,7 +208,10 @@ def test_tensor_path_parity(knn, case, metric):
     assert idx.stat("path") == 2 and idx.stat("gemm_launches") >= 1
     assert idx.stat("overflow_batches") == 0
     D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
-    check_parity(D, I, D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-3)
+    # L2 on unnormalised rows: |x|^2+|y|^2 ~ 6000, so the fp32 expansion formula resolves distances to
+    # ~5e-4 only - comparable to the gaps between consecutive neighbours at k >= 1000; more positions
+    # are legitimately undecidable in fp32 (still arbitrated one by one in fp64 by check_parity).
+    check_parity(D, I, D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-3 if metric == IP else 1e-2)
     # the rerank repeats the scan kernel's arithmetic: both device paths agree bit for bit
     D1, I1, _ = _search(knn, xq, xb, k, metric, path=1)
     assert np.array_equal(I1, I)
