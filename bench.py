@@ -1,0 +1,301 @@
+#!/usr/bin/env python3
+"""Benchmark of the flat-search hot path (BASELINE.json: queries/s at 1024-d, k=100).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config C4 of BASELINE.json / SURVEY.md section 8d): synthetic 10M x 1024 fp32
+database of L2-normalised N(0,1) rows (seeded per 65536-row block, so any GPU count builds
+the same database), 100k normalised queries, k = 100, inner product.  One "step" = one full
+pass of index.search over all queries.  With N GPUs the database is row-sharded (strong
+scaling: total work fixed), every rank scores all queries against its shard, results are
+all-gathered over NCCL and merged on the device.
+
+Legs, all in one JSON line printed by rank 0:
+  value     queries/s with the queries already resident in HBM (device-pointer C-ABI call)
+  e2e       same through the host-pointer C-ABI call: pinned host queries -> H2D -> search -> D2H
+  roofline  the tcgen05 GEMM kernel: 2*nq*N*d flop / CUDA-event time of its launches
+  cpu_baseline  blocked sgemm + top-k on the host cores (bounded sample, scaled by N)
+--impl reference times the CPU implementation only (see oracle/cpu_baseline.py).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+for p in (str(REPO), str(REPO / "knn-for-homology_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+D_DIM = 1024
+BLOCK_ROWS = 65536
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nb", type=int, default=10_000_000, help="database rows (C4: 10M)")
+    ap.add_argument("--nq", type=int, default=100_000, help="queries per step (C4: 100k)")
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"tflops_burst": d.get("bf16_tflops"), "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, rank, world):
+    """CPU implementation of the path on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+
+    n_sample, nq_sample = min(args.nb, 400_000), min(args.nq, 2048)
+    res = None
+    times = []
+    for i in range(args.warmup + args.steps):
+        res = cpu_baseline.time_sample(args.nb, D_DIM, args.k, n_sample=n_sample, nq_sample=nq_sample, seed=99 + i)
+        if i >= args.warmup:
+            times.append(res)
+    qps = statistics.mean(r["value"] for r in times)
+    line = {
+        "impl": "reference", "metric": "queries/s at 1024-d, k=%d, exact flat inner-product search" % args.k,
+        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * statistics.mean(r["seconds"] for r in times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    name = "C4" if (args.nb, args.nq, args.k) == (10_000_000, 100_000, 100) else "custom"
+    return {"workload": f"{name}: synthetic normalised {args.nb}x{D_DIM} fp32 database, {args.nq} queries, k={args.k}, "
+                        f"inner product, exact (ids = fp32 IndexFlatIP)",
+            "database_rows": args.nb, "queries_per_step": args.nq, "k": args.k, "d": D_DIM,
+            "sharding": f"rows over {world} GPU(s)", "l2": "inputs larger than L2 (bf16 database shard >> 126 MB)"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import knn_b200
+    from knn_b200.distributed import ShardedIndexFlat, shard_bounds
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- build the database shard on the device (index build is reported, not timed as search) ----
+    t_build = time.perf_counter()
+    index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank)
+    b = shard_bounds(args.nb, world)
+    lo, hi = b[rank], b[rank + 1]
+    index.local.reserve(hi - lo)
+    for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
+        r0, r1 = blk * BLOCK_ROWS, min((blk + 1) * BLOCK_ROWS, args.nb)
+        g = torch.Generator(device=dev).manual_seed(1234 + blk)
+        rows = torch.randn(r1 - r0, D_DIM, device=dev, generator=g)
+        knn_b200.normalize_L2(rows)
+        s0, s1 = max(lo, r0), min(hi, r1)
+        index.local.add(rows[s0 - r0:s1 - r0])
+    index.adopt_local(global_start=lo, n_global=args.nb)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
+
+    g = torch.Generator(device=dev).manual_seed(4321)
+    xq_dev = torch.randn(args.nq, D_DIM, device=dev, generator=g)
+    knn_b200.normalize_L2(xq_dev)
+    xq_host = torch.empty((args.nq, D_DIM), dtype=torch.float32, pin_memory=True)
+    xq_host.copy_(xq_dev)
+    D_host = torch.empty((args.nq, args.k), dtype=torch.float32, pin_memory=True)
+    I_host = torch.empty((args.nq, args.k), dtype=torch.int64, pin_memory=True)
+    torch.cuda.synchronize()
+
+    lib = knn_b200._lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return index.search(xq_dev, args.k)
+
+    def step_e2e():
+        if world == 1:
+            # the raw host-pointer C-ABI call: H2D of the queries, search, D2H of (D, I)
+            index.local.search_into(xq_host.data_ptr(), args.nq, args.k, D_host.data_ptr(), I_host.data_ptr())
+        else:
+            xq = xq_host.to(dev, non_blocking=True)
+            D, I = index.search(xq, args.k)
+            if rank == 0:
+                D_host.copy_(D, non_blocking=True)
+                I_host.copy_(I, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        index.local.set_param("profile", 1 if profile else 0)
+        barrier()
+        launches0 = lib.knn_kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gemm_ms, gemm_launches = 0.0, 0
+        e0.record()
+        for _ in range(steps):
+            fn()
+            if profile:
+                gemm_ms += index.local.stat("gemm_ms")
+                gemm_launches += int(index.local.stat("gemm_launches"))
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.knn_kernel_launches() - launches0
+        index.local.set_param("profile", 0)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, gemm_ms, gemm_launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, gemm_ms, gemm_launches = timed(step_device, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.nq * args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e, _, _, _ = timed(step_e2e, args.steps, 1)
+        h2d = args.nq * D_DIM * 4
+        d2h = args.nq * args.k * 12
+        e2e = {"value": args.nq * args.steps / (ms_e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps}
+
+    # parity spot check inside the bench: a few queries rescored exhaustively by the exact fp32 path
+    D, I = step_device()
+    search_path = int(index.local.stat("path"))
+    chk = torch.arange(0, args.nq, max(1, args.nq // 64), device=dev)[:64]
+    index.local.set_param("path", 1)
+    D1, I1 = index.search(xq_dev[chk].contiguous(), args.k)
+    index.local.set_param("path", 0)
+    parity_ok = bool(torch.equal(I[chk], I1) and torch.equal(D[chk], D1))
+
+    if rank == 0:
+        peaks = measured_peaks()
+        n_shard = hi - lo
+        flops_per_step = 2.0 * args.nq * n_shard * D_DIM
+        achieved = flops_per_step * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        peak = peaks["tflops_sustained"]
+        roofline = {"bound": "tensor", "kernel": "gemm_filter_kernel (tcgen05 bf16, fused threshold filter)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if achieved else None, "peak_kind": "sustained, " + peaks["source"],
+                    "frac_of_burst": (achieved / peaks["tflops_burst"]) if achieved else None,
+                    "traffic": None, "launches": gemm_launches, "kernel_ms_per_step": gemm_ms / args.steps,
+                    "algorithmic_flop_per_launch_avg": flops_per_step * args.steps / max(1, gemm_launches)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_baseline
+
+            cpu = cpu_baseline.time_sample(args.nb, D_DIM, args.k, n_sample=min(args.nb, 400_000),
+                                           nq_sample=min(args.nq, 4096))
+            cpu = {k: cpu[k] for k in ["value", "unit", "cores", "kind", "sample"]}
+        line = {
+            "metric": "queries/s at 1024-d, k=%d, exact flat inner-product search" % args.k,
+            "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 tensor-core filter + f32 exact rerank", "data": "synthetic",
+            "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
+            "search_path": search_path,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

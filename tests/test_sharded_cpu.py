@@ -1,0 +1,97 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: row split, local->global id
+mapping across several add() calls, all-gather, merge call.  The per-shard search and the merge
+kernel are CUDA-only in the product, so this test injects the oracle as the shard engine and a
+numpy merge with the same tie rule - it checks the plumbing, not the kernels (those are covered
+by tests/test_gpu_parity.py::test_torch_device_api_and_merge)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+class _OracleShard:
+    def __init__(self, d, metric):
+        from oracle import flat_oracle as fo
+
+        self.ix = fo.IndexFlat(d, metric)
+        self.device = 0
+
+    @property
+    def ntotal(self):
+        return self.ix.ntotal
+
+    def add(self, x):
+        self.ix.add(np.ascontiguousarray(x, dtype=np.float32))
+
+    def search(self, x, k):
+        return self.ix.search(np.ascontiguousarray(x, dtype=np.float32), k)
+
+
+def _merge_numpy(Dg, Ig, metric):
+    w, nq, k = Dg.shape
+    D = Dg.permute(1, 0, 2).reshape(nq, w * k).numpy()
+    I = Ig.permute(1, 0, 2).reshape(nq, w * k).numpy()
+    key = np.where(I < 0, np.inf, -D if metric == 0 else D)
+    outD = np.empty((nq, k), np.float32)
+    outI = np.empty((nq, k), np.int64)
+    for r in range(nq):
+        order = np.lexsort((I[r], key[r]))[:k]
+        outD[r], outI[r] = D[r, order], I[r, order]
+    return torch.from_numpy(outD), torch.from_numpy(outI)
+
+
+def _worker(rank, world, port, metric, out):
+    sys.path.insert(0, str(REPO))
+    sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from knn_b200.distributed import ShardedIndexFlat
+    from oracle import flat_oracle as fo
+
+    rng = np.random.default_rng(0)
+    xb = rng.standard_normal((1001, 32)).astype(np.float32)
+    xq = rng.standard_normal((17, 32)).astype(np.float32)
+    index = ShardedIndexFlat(32, metric, index_factory=lambda: _OracleShard(32, metric), merge_fn=_merge_numpy)
+    index.add(xb[:300])      # three adds: ids must stay positions in the concatenation
+    index.add(xb[300:301])
+    index.add(xb[301:])
+    assert index.ntotal == 1001
+    assert index.local.ntotal in (500, 501)
+    for k in (5, 1001 // 2, 1200):  # last one: k > ntotal -> -1 padding survives the merge
+        D, I = index.search(xq, k)
+        D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+        assert np.array_equal(I, I_ref), (rank, k)
+        assert np.array_equal(D, D_ref), (rank, k)
+    if rank == 0:
+        Path(out).write_text("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_sharded_index_world2_gloo(tmp_path, metric):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = tmp_path / "ok"
+    mp.spawn(_worker, args=(2, port, metric, str(out)), nprocs=2, join=True)
+    assert out.read_text() == "ok"
+
+
+def test_shard_bounds_cover_everything():
+    sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
+    from knn_b200.distributed import shard_bounds
+
+    for n in (0, 1, 7, 10_000_000):
+        for w in (1, 2, 4, 8):
+            b = shard_bounds(n, w)
+            assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+            assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) <= 1
