@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--nb", type=int, default=10_000_000, help="database rows (C4: 10M)")
     ap.add_argument("--nq", type=int, default=100_000, help="queries per step (C4: 100k)")
     ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--cta-group", type=int, default=2, choices=[1, 2], help="tcgen05 cta_group of the GEMM kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -172,6 +173,7 @@ def main():
     index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank)
     b = shard_bounds(args.nb, world)
     lo, hi = b[rank], b[rank + 1]
+    index.local.set_param("cta_group", args.cta_group)
     index.local.reserve(hi - lo)
     for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
         r0, r1 = blk * BLOCK_ROWS, min((blk + 1) * BLOCK_ROWS, args.nb)
@@ -289,7 +291,7 @@ def main():
             "dtype": "bf16 tensor-core filter + f32 exact rerank", "data": "synthetic",
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
-            "search_path": search_path,
+            "search_path": search_path, "cta_group": args.cta_group,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

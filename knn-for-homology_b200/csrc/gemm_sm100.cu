@@ -9,10 +9,15 @@
 // oracle/flat_oracle.py).  Scores produced here are approximate (bf16 inputs); the candidate
 // threshold carries the error bound and the survivors are rescored in fp32 (rerank_kernel).
 //
-// Tile: 128 queries (MMA M, TMEM lanes) x 256 database rows (MMA N, TMEM columns) x 64 (one
-// 128-byte swizzle atom of K per pipeline stage).  Warp roles: 0 = TMA producer, 1 = MMA issuer
-// (+ TMEM allocator), 2..5 = epilogue (one TMEM lane quarter each).  Persistent CTAs, static
-// tile schedule with the query tile fastest so that co-resident CTAs share database tiles in L2.
+// Tile per CTA: 128 queries (TMEM lanes) x 256 database rows (TMEM columns) x 64 (one 128-byte
+// swizzle atom of K per pipeline stage).  Two variants of the same kernel:
+//   CG = 1  one CTA per tile, tcgen05.mma.cta_group::1, M = 128, 4 stages of 48 KB;
+//   CG = 2  a CTA pair (cluster of 2) per 256 x 256 tile, tcgen05.mma.cta_group::2, M = 256: each
+//           CTA stages its 128 query rows and HALF of the database tile (128 rows), the pair's
+//           tensor cores read both halves -> half the database bytes per CTA, 6 stages of 32 KB.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator; leader CTA only issues),
+// 2..5 = epilogue (one TMEM lane quarter each).  Persistent CTAs, static tile schedule with the
+// query tile fastest so that co-resident CTAs share database tiles in L2.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -21,17 +26,28 @@ namespace knn {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BM = 128;   // query rows per CTA
+constexpr int BN = 256;   // database rows per tile
 constexpr int BK = 64;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;
-constexpr uint32_t kBytesA = BM * BK * 2;
-constexpr uint32_t kBytesB = BN * BK * 2;
-constexpr uint32_t kBytesStage = kBytesA + kBytesB;
-constexpr size_t kSmemBytes = size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
+
+template <int CG>
+struct Cfg {
+    static constexpr int kStages = CG == 1 ? 4 : 6;
+    static constexpr int kRowsB = BN / CG;  // database rows staged by one CTA
+    static constexpr uint32_t kBytesA = BM * BK * 2;
+    static constexpr uint32_t kBytesB = kRowsB * BK * 2;
+    static constexpr uint32_t kBytesStage = kBytesA + kBytesB;
+    static constexpr size_t kSmemBytes = size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/;
+    // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+    // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 (M = 256 for a CTA pair).
+    static constexpr uint32_t kInstrDesc =
+        (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t((BM * CG) >> 4) << 24);
+};
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -63,40 +79,101 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+// L2 eviction-priority policies (the encodings CUTLASS passes as TMA cache hints)
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // database tiles: streamed once per query batch
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // query tiles: re-read for every database tile
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
             smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
+}
+// CTA-pair variant: both CTAs load into their own shared memory, the bytes are accounted on the
+// LEADER CTA's barrier (peer bit cleared), where the MMA issuer waits.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    } else {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    }
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x 256 x 16 bf16 MMA
+// D[tmem] (+)= A[smem] * B[smem]^T: one (128*CG) x 256 x 16 bf16 MMA (CG = 2: across the CTA pair)
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
-// arrives on the mbarrier once all MMAs issued so far by this thread have completed
+// arrives on the mbarrier (CG = 2: on the barrier at this offset in BOTH CTAs of the pair) once all
+// MMAs issued so far by this thread have completed
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"(uint16_t(3))
+                     : "memory");
+    }
 }
 
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -127,13 +204,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
-// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-
 struct __align__(8) Barriers {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
     uint64_t acc_full[kAccStages];
     uint64_t acc_empty[kAccStages];
     uint32_t tmem_base;
@@ -141,7 +214,7 @@ struct __align__(8) Barriers {
 
 struct GemmArgs {
     int64_t nq;        // real queries (rows >= nq of the padded query matrix are ignored)
-    int m_tiles;       // nq_pad / 128
+    int m_tiles;       // nq_pad / (128 * CG)
     int n_tiles;       // ceil((j1 - j0) / 256)
     int num_kb;        // dp / 64
     int64_t j0, j1;    // database rows of this panel
@@ -153,83 +226,109 @@ struct GemmArgs {
     int cap;
 };
 
-template <bool L2, bool DENSE>
+template <bool L2>
+__device__ __forceinline__ void load_scores(uint32_t taddr, int64_t j_first, const GemmArgs& args, float (&v)[32]) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r[i]);
+        if (L2) {
+            const int64_t j = j_first + i;
+            v[i] = 2.0f * v[i] - (j < args.j1 ? __ldg(args.ynorm2 + j) : 0.f);
+        }
+    }
+}
+
+template <int CG, bool L2, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
+    using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + size_t(kStages) * kBytesStage);
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + size_t(C::kStages) * C::kBytesStage);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = args.m_tiles * args.n_tiles;
+    const uint32_t cta_rank = CG == 1 ? 0u : cluster_ctarank();  // position in the CTA pair
+    const bool leader = cta_rank == 0;
+    const int unit = CG == 1 ? blockIdx.x : (blockIdx.x >> 1);   // tile-scheduling unit (CTA or CTA pair)
+    const int num_units = CG == 1 ? gridDim.x : (gridDim.x >> 1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_q);
         prefetch_tmap(&map_db);
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < C::kStages; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->empty[i], 1);
         }
         for (int i = 0; i < kAccStages; ++i) {
             mbar_init(&bars->acc_full[i], 1);
-            mbar_init(&bars->acc_empty[i], 4);  // one arrival per epilogue warp
+            mbar_init(&bars->acc_empty[i], 4 * CG);  // one arrival per epilogue warp of every CTA on the tile
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    if (warp == 1) tmem_alloc<CG>(&bars->tmem_base, kTmemCols);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();  // peer barriers must exist before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA loads its own query rows and its share of the database tile) =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
                 const int mt = tile % args.m_tiles;
                 const int nt = tile / args.m_tiles;
-                const int row_q = mt * BM;
-                const int row_db = int(args.j0) + nt * BN;
+                const int row_q = mt * (BM * CG) + int(cta_rank) * BM;
+                const int row_db = int(args.j0) + nt * BN + int(cta_rank) * C::kRowsB;
                 for (int kb = 0; kb < args.num_kb; ++kb) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + size_t(stage) * kBytesStage;
-                    uint8_t* sb = sa + kBytesA;
-                    mbar_expect_tx(&bars->full[stage], kBytesStage);
-                    tma_load_2d(sa, &map_q, &bars->full[stage], kb * BK, row_q);
-                    tma_load_2d(sb, &map_db, &bars->full[stage], kb * BK, row_db);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    uint8_t* sa = smem + size_t(stage) * C::kBytesStage;
+                    uint8_t* sb = sa + C::kBytesA;
+                    if constexpr (CG == 1) {
+                        mbar_expect_tx(&bars->full[stage], C::kBytesStage);
+                        tma_load_2d(sa, &map_q, &bars->full[stage], kb * BK, row_q, kEvictLast);
+                        tma_load_2d(sb, &map_db, &bars->full[stage], kb * BK, row_db, kEvictFirst);
+                    } else {
+                        if (leader) mbar_expect_tx(&bars->full[stage], C::kBytesStage * 2);  // both CTAs' bytes
+                        tma_load_2d_pair(sa, &map_q, &bars->full[stage], kb * BK, row_q, kEvictLast);
+                        tma_load_2d_pair(sb, &map_db, &bars->full[stage], kb * BK, row_db, kEvictFirst);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (one thread; for a CTA pair only the leader issues, for both CTAs) =====
+        if (lane == 0 && leader) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
                 for (int kb = 0; kb < args.num_kb; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + size_t(stage) * kBytesStage);
-                    const uint32_t sb = sa + kBytesA;
+                    const uint32_t sa = smem_u32(smem + size_t(stage) * C::kBytesStage);
+                    const uint32_t sb = sa + C::kBytesA;
                     const uint64_t da = make_smem_desc(sa);
                     const uint64_t db = make_smem_desc(sb);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
-                        umma_bf16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
+                        umma_bf16<CG>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), C::kInstrDesc, (kb | k) ? 1u : 0u);
                     }
-                    umma_commit(&bars->empty[stage]);  // smem slot reusable once these MMAs have read it
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    umma_commit<CG>(&bars->empty[stage]);  // smem slot reusable once these MMAs have read it
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&bars->acc_full[acc]);  // accumulator complete -> epilogue
+                umma_commit<CG>(&bars->acc_full[acc]);  // accumulator complete -> epilogue (of both CTAs)
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -238,32 +337,22 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
             const int mt = tile % args.m_tiles;
             const int nt = tile / args.m_tiles;
-            const int64_t q = int64_t(mt) * BM + quarter * 32 + lane;
+            const int64_t q = int64_t(mt) * (BM * CG) + int64_t(cta_rank) * BM + quarter * 32 + lane;
             const int64_t jbase = args.j0 + int64_t(nt) * BN;
             const bool q_ok = q < args.nq;
             const float thr = q_ok ? args.thr[q] : FLT_MAX;
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
+            if constexpr (DENSE) {
 #pragma unroll 1
-            for (int cg = 0; cg < BN / 32; ++cg) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + uint32_t(cg * 32), r);
-                tmem_ld_wait();
-                const int64_t j_first = jbase + cg * 32;
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = __uint_as_float(r[i]);
-                    if (L2) {
-                        const int64_t j = j_first + i;
-                        v[i] = 2.0f * v[i] - (j < args.j1 ? __ldg(args.ynorm2 + j) : 0.f);
-                    }
-                }
-                if (DENSE) {
+                for (int cg = 0; cg < BN / 32; ++cg) {
+                    float v[32];
+                    load_scores<L2>(taddr + uint32_t(cg * 32), jbase + cg * 32, args, v);
+                    const int64_t j_first = jbase + cg * 32;
                     if (q_ok) {
                         float* cs = args.cand_scores + q * int64_t(args.cap) + (j_first - args.j0);
                         uint32_t* ci = args.cand_ids + q * int64_t(args.cap) + (j_first - args.j0);
@@ -284,37 +373,80 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                             }
                         }
                     }
-                } else {
+                    __syncwarp();  // reconverge before the next warp-wide tcgen05.ld
+                }
+            } else {
+                // Pass A: one compare per score; count this query's survivors in the tile.  Survivors are
+                // rare once the threshold has tightened, so the common path is LDTM + 32 FSETP per group.
+                int cnt = 0;
+                uint32_t flagged = 0;  // warp-uniform: column groups in which some lane has a survivor
+#pragma unroll 1
+                for (int cg = 0; cg < BN / 32; ++cg) {
+                    float v[32];
+                    load_scores<L2>(taddr + uint32_t(cg * 32), jbase + cg * 32, args, v);
+                    const int64_t j_first = jbase + cg * 32;
                     bool any = false;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) any |= (v[i] >= thr);
-                    if (any) {
+                    if (__any_sync(0xffffffffu, any)) {
+                        flagged |= 1u << cg;
+                        if (any) {
+                            if (j_first + 32 <= args.j1) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) cnt += (v[i] >= thr) ? 1 : 0;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) cnt += (v[i] >= thr && j_first + i < args.j1) ? 1 : 0;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (flagged) {  // warp-uniform
+                    // one reservation per query and tile (all lanes' atomics are in flight together), then
+                    // Pass B re-reads the flagged groups from TMEM and stores the survivors
+                    int pos = 0;
+                    if (cnt > 0) pos = atomicAdd(args.counts + q, cnt);
+                    float* cs = args.cand_scores + q * int64_t(args.cap);
+                    uint32_t* ci = args.cand_ids + q * int64_t(args.cap);
+                    while (flagged) {
+                        const int cg = __ffs(int(flagged)) - 1;
+                        flagged &= flagged - 1;
+                        float v[32];
+                        load_scores<L2>(taddr + uint32_t(cg * 32), jbase + cg * 32, args, v);
+                        const int64_t j_first = jbase + cg * 32;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             if (v[i] >= thr && j_first + i < args.j1) {
-                                const int pos = atomicAdd(args.counts + q, 1);
                                 if (pos < args.cap) {
-                                    args.cand_scores[q * int64_t(args.cap) + pos] = v[i];
-                                    args.cand_ids[q * int64_t(args.cap) + pos] = uint32_t(j_first + i);
+                                    cs[pos] = v[i];
+                                    ci[pos] = uint32_t(j_first + i);
                                 }
+                                ++pos;
                             }
                         }
+                        __syncwarp();
                     }
                 }
-                __syncwarp();  // reconverge before the next warp-wide tcgen05.ld
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+            if (lane == 0) {
+                // the accumulator stage may be overwritten once every epilogue warp of every CTA on this
+                // tile has drained it; the MMA issuer waits on the leader's barrier
+                if constexpr (CG == 1) mbar_arrive(&bars->acc_empty[acc]);
+                else mbar_arrive_remote(&bars->acc_empty[acc], 0);
+            }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    // nobody may leave (or free TMEM) while the peer can still read this CTA's shared memory or signal its barriers
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc<CG>(tmem_base, kTmemCols);
     }
 }
 
@@ -327,8 +459,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct GemmPlan {
     EncodeTiledFn encode = nullptr;
     int sms = 148;
-    bool attrs_set = false;
+    int cta_group = 2;  // 1: one CTA per tile, 2: CTA pairs (tcgen05 cta_group::2)
 };
+
+void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
+int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
     GemmPlan* p = new GemmPlan();
@@ -371,12 +506,41 @@ static int make_map(GemmPlan* p, CUtensorMap* map, const __nv_bfloat16* base, in
     return KNN_OK;
 }
 
+template <int CG, bool L2, bool DENSE>
+static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorMap& map_db, const GemmArgs& a, cudaStream_t s) {
+    auto kern = gemm_filter_kernel<CG, L2, DENSE>;
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<CG>::kSmemBytes)));
+        attr_done = true;
+    }
+    const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;
+    const int units_max = p->sms / CG;
+    const int units = int(tiles < units_max ? tiles : units_max);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(units * CG), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<CG>::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_q, map_db, a));
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
 int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, int64_t nq_pad, int dp,
                        const __nv_bfloat16* xb_bf16, int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1,
                        int metric, bool dense_first, FilterState st, cudaStream_t s) {
     if (j1 <= j0 || nq <= 0) return KNN_OK;
-    if (dp % BK != 0 || nq_pad % BM != 0) {
-        set_error("gemm_filter: dp (%d) must be a multiple of %d and nq_pad (%lld) of %d", dp, BK, (long long)nq_pad, BM);
+    const int cg = p->cta_group;
+    if (dp % BK != 0 || nq_pad % (BM * cg) != 0) {
+        set_error("gemm_filter: dp (%d) must be a multiple of %d and nq_pad (%lld) of %d", dp, BK, (long long)nq_pad, BM * cg);
         return KNN_ERR_INVALID;
     }
     if (dense_first && j1 - j0 > st.cap) {
@@ -385,10 +549,10 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
     }
     CUtensorMap map_q, map_db;
     KNN_CHECK(make_map(p, &map_q, xq_bf16, nq_pad, dp, BM));
-    KNN_CHECK(make_map(p, &map_db, xb_bf16, ntotal, dp, BN));
+    KNN_CHECK(make_map(p, &map_db, xb_bf16, ntotal, dp, BN / cg));
     GemmArgs a;
     a.nq = nq;
-    a.m_tiles = int(nq_pad / BM);
+    a.m_tiles = int(nq_pad / (BM * cg));
     a.n_tiles = int((j1 - j0 + BN - 1) / BN);
     a.num_kb = dp / BK;
     a.j0 = j0;
@@ -399,25 +563,17 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
     a.cand_scores = st.cand_scores;
     a.cand_ids = st.cand_ids;
     a.cap = st.cap;
-    const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;
-    const int grid = int(tiles < p->sms ? tiles : p->sms);
     const bool l2 = metric == KNN_METRIC_L2;
-    if (!p->attrs_set) {
-        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-        KNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-        p->attrs_set = true;
+#define KNN_GEMM_DISPATCH(CGV)                                                                        \
+    if (l2) {                                                                                         \
+        return dense_first ? launch_variant<CGV, true, true>(p, map_q, map_db, a, s)                  \
+                           : launch_variant<CGV, true, false>(p, map_q, map_db, a, s);                \
+    } else {                                                                                          \
+        return dense_first ? launch_variant<CGV, false, true>(p, map_q, map_db, a, s)                 \
+                           : launch_variant<CGV, false, false>(p, map_q, map_db, a, s);               \
     }
-    if (l2) {
-        if (dense_first) gemm_filter_kernel<true, true><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
-        else gemm_filter_kernel<true, false><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
-    } else {
-        if (dense_first) gemm_filter_kernel<false, true><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
-        else gemm_filter_kernel<false, false><<<grid, kThreads, kSmemBytes, s>>>(map_q, map_db, a);
-    }
-    KNN_CHECK_LAUNCH();
-    return KNN_OK;
+    if (cg == 1) { KNN_GEMM_DISPATCH(1) } else { KNN_GEMM_DISPATCH(2) }
+#undef KNN_GEMM_DISPATCH
 }
 
 }  // namespace knn

@@ -97,6 +97,7 @@ struct knn_index {
     int64_t query_batch = 16384;
     int profile = 0;
     int64_t tensor_min_nq = 64, tensor_min_n = 8192;
+    int cta_group = 2;
     // statistics of the last search
     int last_path = 0;
     long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_rerank_pairs = 0;
@@ -209,7 +210,7 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     const int64_t first_panel = N < cap / 2 ? N : cap / 2;
     int64_t qb = ix->query_batch;
     if (qb > nq) qb = nq;
-    qb = round_up(qb, 128);
+    qb = round_up(qb, 256);
     const int64_t qpad = qb;
     KNN_CHECK(ix->xq_f32.ensure(size_t(qpad) * ix->dp * sizeof(float)));
     KNN_CHECK(ix->xq_bf16.ensure(size_t(qpad) * ix->dp * sizeof(__nv_bfloat16)));
@@ -228,10 +229,11 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     st.cap = cap;
     int* d_overflow = ix->overflow.as<int>();
     if (!ix->plan) KNN_CHECK(gemm_plan_create(&ix->plan, ix->device));
+    gemm_plan_set_cta_group(ix->plan, ix->cta_group);
 
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
-        const int64_t nb_pad = round_up(nb, 128);
+        const int64_t nb_pad = round_up(nb, 256);
         KNN_CHECK_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int) * 2, s));
         KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb_pad, ix->d, ix->dp, ix->xq_f32.as<float>(),
                                       ix->xq_bf16.as<__nv_bfloat16>(), ix->xnorm2.as<float>(), ix->eps.as<float>(),
@@ -578,8 +580,9 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     if (!ix || !name) return KNN_ERR_INVALID;
     std::string n(name);
     if (n == "path" && value >= 0 && value <= 2) ix->path_param = int(value);
-    else if (n == "query_batch" && value >= 128) ix->query_batch = round_up(value, 128);
+    else if (n == "query_batch" && value >= 128) ix->query_batch = round_up(value, 256);
     else if (n == "profile") ix->profile = value != 0;
+    else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
     else {

@@ -199,12 +199,14 @@ TENSOR_CASES = [
 ]
 
 
+@pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("metric", [IP, L2])
 @pytest.mark.parametrize("case", TENSOR_CASES)
-def test_tensor_path_parity(knn, case, metric):
+def test_tensor_path_parity(knn, case, metric, cta_group):
+    """cta_group 1: one CTA per 128x256 tile; 2: CTA pairs on 256x256 tiles (tcgen05 cta_group::2)."""
     nq, nb, d, k, qb = case
     xq, xb = _data(nq, nb, d, seed=7 * nq + nb, normalize=metric == IP, scale=1.7)
-    D, I, idx = _search(knn, xq, xb, k, metric, path=2, query_batch=qb)
+    D, I, idx = _search(knn, xq, xb, k, metric, path=2, query_batch=qb, cta_group=cta_group)
     assert idx.stat("path") == 2 and idx.stat("gemm_launches") >= 1
     assert idx.stat("overflow_batches") == 0
     D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
