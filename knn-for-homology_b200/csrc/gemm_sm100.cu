@@ -82,6 +82,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // L2 eviction-priority policies (the encodings CUTLASS passes as TMA cache hints)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // database tiles: streamed once per query batch
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // query tiles: re-read for every database tile
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
     asm volatile(
@@ -224,6 +225,7 @@ struct GemmArgs {
     float* cand_scores;
     uint32_t* cand_ids;
     int cap;
+    uint64_t hint_q, hint_db;  // L2 eviction-priority policies of the two TMA streams
 };
 
 template <bool L2>
@@ -291,12 +293,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     uint8_t* sb = sa + C::kBytesA;
                     if constexpr (CG == 1) {
                         mbar_expect_tx(&bars->full[stage], C::kBytesStage);
-                        tma_load_2d(sa, &map_q, &bars->full[stage], kb * BK, row_q, kEvictLast);
-                        tma_load_2d(sb, &map_db, &bars->full[stage], kb * BK, row_db, kEvictFirst);
+                        tma_load_2d(sa, &map_q, &bars->full[stage], kb * BK, row_q, args.hint_q);
+                        tma_load_2d(sb, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
                     } else {
                         if (leader) mbar_expect_tx(&bars->full[stage], C::kBytesStage * 2);  // both CTAs' bytes
-                        tma_load_2d_pair(sa, &map_q, &bars->full[stage], kb * BK, row_q, kEvictLast);
-                        tma_load_2d_pair(sb, &map_db, &bars->full[stage], kb * BK, row_db, kEvictFirst);
+                        tma_load_2d_pair(sa, &map_q, &bars->full[stage], kb * BK, row_q, args.hint_q);
+                        tma_load_2d_pair(sb, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -460,9 +462,11 @@ struct GemmPlan {
     EncodeTiledFn encode = nullptr;
     int sms = 148;
     int cta_group = 2;  // 1: one CTA per tile, 2: CTA pairs (tcgen05 cta_group::2)
+    int l2_hints = 0;   // 1: queries evict-last, database evict-first
 };
 
 void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
+void gemm_plan_set_l2_hints(GemmPlan* p, int on) { p->l2_hints = on; }
 int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
@@ -563,6 +567,8 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
     a.cand_scores = st.cand_scores;
     a.cand_ids = st.cand_ids;
     a.cap = st.cap;
+    a.hint_q = p->l2_hints ? kEvictLast : kEvictNormal;
+    a.hint_db = p->l2_hints ? kEvictFirst : kEvictNormal;
     const bool l2 = metric == KNN_METRIC_L2;
 #define KNN_GEMM_DISPATCH(CGV)                                                                        \
     if (l2) {                                                                                         \

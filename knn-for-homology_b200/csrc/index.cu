@@ -98,6 +98,7 @@ struct knn_index {
     int profile = 0;
     int64_t tensor_min_nq = 64, tensor_min_n = 8192;
     int cta_group = 2;
+    int l2_hints = 0;
     // statistics of the last search
     int last_path = 0;
     long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_rerank_pairs = 0;
@@ -230,6 +231,7 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     int* d_overflow = ix->overflow.as<int>();
     if (!ix->plan) KNN_CHECK(gemm_plan_create(&ix->plan, ix->device));
     gemm_plan_set_cta_group(ix->plan, ix->cta_group);
+    gemm_plan_set_l2_hints(ix->plan, ix->l2_hints);
 
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
@@ -583,6 +585,7 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "query_batch" && value >= 128) ix->query_batch = round_up(value, 256);
     else if (n == "profile") ix->profile = value != 0;
     else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
+    else if (n == "l2_hints") ix->l2_hints = value != 0;
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
     else {
