@@ -226,6 +226,7 @@ struct GemmArgs {
     uint32_t* cand_ids;
     int cap;
     uint64_t hint_q, hint_db;  // L2 eviction-priority policies of the two TMA streams
+    int debug_skip_epilogue;   // experiments only: accumulators are not read (results are then meaningless)
 };
 
 template <bool L2>
@@ -349,7 +350,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
-            if constexpr (DENSE) {
+            if (args.debug_skip_epilogue) {
+                // measurement aid: main loop only
+            } else if constexpr (DENSE) {
 #pragma unroll 1
                 for (int cg = 0; cg < BN / 32; ++cg) {
                     float v[32];
@@ -463,10 +466,12 @@ struct GemmPlan {
     int sms = 148;
     int cta_group = 2;  // 1: one CTA per tile, 2: CTA pairs (tcgen05 cta_group::2)
     int l2_hints = 0;   // 1: queries evict-last, database evict-first
+    int debug_skip_epilogue = 0;
 };
 
 void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
 void gemm_plan_set_l2_hints(GemmPlan* p, int on) { p->l2_hints = on; }
+void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue) { p->debug_skip_epilogue = skip_epilogue; }
 int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
@@ -567,6 +572,7 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
     a.cand_scores = st.cand_scores;
     a.cand_ids = st.cand_ids;
     a.cap = st.cap;
+    a.debug_skip_epilogue = p->debug_skip_epilogue;
     a.hint_q = p->l2_hints ? kEvictLast : kEvictNormal;
     a.hint_db = p->l2_hints ? kEvictFirst : kEvictNormal;
     const bool l2 = metric == KNN_METRIC_L2;

@@ -89,9 +89,16 @@ struct knn_index {
     cudaStream_t stream = nullptr;
     cudaEvent_t add_event = nullptr;  // last ingest; searches on another stream wait on it
     GemmPlan* plan = nullptr;
-    // workspaces
-    DevBuf stage, xq_f32, xq_bf16, xnorm2, eps, thr, counts, cand_s, cand_i, scores, lists_s, lists_i, overflow;
+    // workspaces: exact path / staging
+    DevBuf stage, xq_f32, xnorm2, eps, scores, lists_s, lists_i, overflow;
     DevBuf h_xq, h_D, h_I;
+    // tensor path: two query batches are in flight on two streams (the CUDA-core kernels of one
+    // batch - tighten, rerank, select - run under the tensor-core GEMM of the other)
+    struct BatchWs {
+        DevBuf xq_f32, xq_bf16, xnorm2, eps, thr, counts, cand_s, cand_i;
+    } bws[2];
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     // parameters
     int path_param = 0;
     int64_t query_batch = 16384;
@@ -99,6 +106,8 @@ struct knn_index {
     int64_t tensor_min_nq = 64, tensor_min_n = 8192;
     int cta_group = 2;
     int l2_hints = 0;
+    int streams = 2;
+    int debug_skip_epilogue = 0;
     // statistics of the last search
     int last_path = 0;
     long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_rerank_pairs = 0;
@@ -202,6 +211,16 @@ int search_exact(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D
 }
 
 // ---- tensor path --------------------------------------------------------------------------
+int ensure_aux(knn_index* ix) {
+    if (ix->aux[0]) return KNN_OK;
+    for (int i = 0; i < 2; ++i) {
+        KNN_CHECK_CUDA(cudaStreamCreateWithFlags(&ix->aux[i], cudaStreamNonBlocking));
+        KNN_CHECK_CUDA(cudaEventCreateWithFlags(&ix->ev_join[i], cudaEventDisableTiming));
+    }
+    KNN_CHECK_CUDA(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
+    return KNN_OK;
+}
+
 int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
                   cudaStream_t s) {
     const int largest = ix->metric == KNN_METRIC_INNER_PRODUCT;
@@ -212,35 +231,50 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     int64_t qb = ix->query_batch;
     if (qb > nq) qb = nq;
     qb = round_up(qb, 256);
-    const int64_t qpad = qb;
-    KNN_CHECK(ix->xq_f32.ensure(size_t(qpad) * ix->dp * sizeof(float)));
-    KNN_CHECK(ix->xq_bf16.ensure(size_t(qpad) * ix->dp * sizeof(__nv_bfloat16)));
-    KNN_CHECK(ix->xnorm2.ensure(size_t(qpad) * sizeof(float)));
-    KNN_CHECK(ix->eps.ensure(size_t(qpad) * sizeof(float)));
-    KNN_CHECK(ix->thr.ensure(size_t(qpad) * sizeof(float)));
-    KNN_CHECK(ix->counts.ensure(size_t(qpad) * sizeof(int)));
-    KNN_CHECK(ix->cand_s.ensure(size_t(qpad) * cap * sizeof(float)));
-    KNN_CHECK(ix->cand_i.ensure(size_t(qpad) * cap * sizeof(uint32_t)));
-    KNN_CHECK(ix->overflow.ensure(sizeof(int) * 2));
-    FilterState st;
-    st.thr = ix->thr.as<float>();
-    st.counts = ix->counts.as<int>();
-    st.cand_scores = ix->cand_s.as<float>();
-    st.cand_ids = ix->cand_i.as<uint32_t>();
-    st.cap = cap;
+    const int64_t nbatches = (nq + qb - 1) / qb;
+    // event timing of the GEMM launches needs them serialised: profile mode uses one stream
+    const int nstreams = (ix->streams >= 2 && nbatches >= 2 && !ix->profile) ? 2 : 1;
+    for (int w = 0; w < nstreams; ++w) {
+        auto& W = ix->bws[w];
+        KNN_CHECK(W.xq_f32.ensure(size_t(qb) * ix->dp * sizeof(float)));
+        KNN_CHECK(W.xq_bf16.ensure(size_t(qb) * ix->dp * sizeof(__nv_bfloat16)));
+        KNN_CHECK(W.xnorm2.ensure(size_t(qb) * sizeof(float)));
+        KNN_CHECK(W.eps.ensure(size_t(qb) * sizeof(float)));
+        KNN_CHECK(W.thr.ensure(size_t(qb) * sizeof(float)));
+        KNN_CHECK(W.counts.ensure(size_t(qb) * sizeof(int)));
+        KNN_CHECK(W.cand_s.ensure(size_t(qb) * cap * sizeof(float)));
+        KNN_CHECK(W.cand_i.ensure(size_t(qb) * cap * sizeof(uint32_t)));
+    }
+    KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(nbatches)));
     int* d_overflow = ix->overflow.as<int>();
     if (!ix->plan) KNN_CHECK(gemm_plan_create(&ix->plan, ix->device));
     gemm_plan_set_cta_group(ix->plan, ix->cta_group);
     gemm_plan_set_l2_hints(ix->plan, ix->l2_hints);
+    gemm_plan_set_debug(ix->plan, ix->debug_skip_epilogue);
+    KNN_CHECK_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int) * size_t(nbatches), s));
+    if (nstreams == 2) {
+        KNN_CHECK(ensure_aux(ix));
+        KNN_CHECK_CUDA(cudaEventRecord(ix->ev_fork, s));
+        for (int w = 0; w < 2; ++w) KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->aux[w], ix->ev_fork, 0));
+    }
 
-    for (int64_t q0 = 0; q0 < nq; q0 += qb) {
+    for (int64_t b = 0; b < nbatches; ++b) {
+        const int64_t q0 = b * qb;
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
         const int64_t nb_pad = round_up(nb, 256);
-        KNN_CHECK_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int) * 2, s));
-        KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb_pad, ix->d, ix->dp, ix->xq_f32.as<float>(),
-                                      ix->xq_bf16.as<__nv_bfloat16>(), ix->xnorm2.as<float>(), ix->eps.as<float>(),
-                                      ix->stats, ix->metric, s));
-        KNN_CHECK(launch_init_filter(st, nb, nb_pad, int(first_panel), s));
+        const int w = nstreams == 2 ? int(b & 1) : 0;
+        cudaStream_t st_ = nstreams == 2 ? ix->aux[w] : s;
+        auto& W = ix->bws[w];
+        FilterState st;
+        st.thr = W.thr.as<float>();
+        st.counts = W.counts.as<int>();
+        st.cand_scores = W.cand_s.as<float>();
+        st.cand_ids = W.cand_i.as<uint32_t>();
+        st.cap = cap;
+        KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb_pad, ix->d, ix->dp, W.xq_f32.as<float>(),
+                                      W.xq_bf16.as<__nv_bfloat16>(), W.xnorm2.as<float>(), W.eps.as<float>(), ix->stats,
+                                      ix->metric, st_));
+        KNN_CHECK(launch_init_filter(st, nb, nb_pad, int(first_panel), st_));
         int64_t j0 = 0;
         bool first = true;
         while (j0 < N) {
@@ -250,31 +284,40 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
             if (ix->profile) {
                 e0 = next_event(ix);
                 e1 = next_event(ix);
-                cudaEventRecord(e0, s);
+                cudaEventRecord(e0, st_);
             }
-            KNN_CHECK(gemm_filter_launch(ix->plan, ix->xq_bf16.as<__nv_bfloat16>(), nb, nb_pad, ix->dp, ix->xb_bf16, N,
-                                         ix->ynorm2, j0, j1, ix->metric, first, st, s));
-            if (ix->profile) cudaEventRecord(e1, s);
+            KNN_CHECK(gemm_filter_launch(ix->plan, W.xq_bf16.as<__nv_bfloat16>(), nb, nb_pad, ix->dp, ix->xb_bf16, N,
+                                         ix->ynorm2, j0, j1, ix->metric, first, st, st_));
+            if (ix->profile) cudaEventRecord(e1, st_);
             ix->st_gemm_launches++;
-            KNN_CHECK(launch_tighten(st, ix->eps.as<float>(), nb, k, 1, nullptr, d_overflow, s));
+            KNN_CHECK(launch_tighten(st, W.eps.as<float>(), nb, k, 1, nullptr, d_overflow + b, st_));
             j0 = j1;
             first = false;
         }
         // thr now holds tau = (k-th best approx score) - 2 eps: rescoring everything at or above it
         // covers the exact top-k.
-        KNN_CHECK(launch_rerank(ix->xq_f32.as<float>(), ix->xnorm2.as<float>(), nb, ix->dp, ix->xb_f32, ix->xb_bf16,
-                                ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
+        KNN_CHECK(launch_rerank(W.xq_f32.as<float>(), W.xnorm2.as<float>(), nb, ix->dp, ix->xb_f32, ix->xb_bf16,
+                                ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, st_));
         KNN_CHECK(launch_select_final(st.cand_scores, st.cand_ids, st.counts, cap, 0, nb, k, largest, D + q0 * k,
-                                      I + q0 * k, id_base, s));
-        int h_overflow[2] = {0, 0};
-        KNN_CHECK_CUDA(cudaMemcpyAsync(h_overflow, d_overflow, sizeof(h_overflow), cudaMemcpyDeviceToHost, s));
-        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
-        if (h_overflow[0]) {
-            // a candidate list ran past its capacity (heavily duplicated / clustered scores):
-            // never truncate silently - redo this batch with the exact scan.
-            ix->st_overflow_batches++;
-            KNN_CHECK(search_exact(ix, nb, xq_dev + q0 * ix->d, k, D + q0 * k, I + q0 * k, id_base, s));
+                                      I + q0 * k, id_base, st_));
+    }
+    if (nstreams == 2) {
+        for (int w = 0; w < 2; ++w) {
+            KNN_CHECK_CUDA(cudaEventRecord(ix->ev_join[w], ix->aux[w]));
+            KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_join[w], 0));
         }
+    }
+    // a candidate list that ran past its capacity (heavily duplicated / clustered scores) is never
+    // truncated silently: that batch is redone with the exact scan.
+    std::vector<int> h_overflow(size_t(nbatches), 0);
+    KNN_CHECK_CUDA(cudaMemcpyAsync(h_overflow.data(), d_overflow, sizeof(int) * size_t(nbatches), cudaMemcpyDeviceToHost, s));
+    KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    for (int64_t b = 0; b < nbatches; ++b) {
+        if (!h_overflow[size_t(b)]) continue;
+        const int64_t q0 = b * qb;
+        const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
+        ix->st_overflow_batches++;
+        KNN_CHECK(search_exact(ix, nb, xq_dev + q0 * ix->d, k, D + q0 * k, I + q0 * k, id_base, s));
     }
     return KNN_OK;
 }
@@ -422,9 +465,19 @@ int knn_index_free(knn_index* ix) {
     if (!ix) return KNN_OK;
     DeviceGuard g(ix->device);
     cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xq_bf16, &ix->xnorm2, &ix->eps, &ix->thr, &ix->counts, &ix->cand_s,
-                      &ix->cand_i, &ix->scores, &ix->lists_s, &ix->lists_i, &ix->overflow, &ix->h_xq, &ix->h_D, &ix->h_I})
+    for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xnorm2, &ix->eps, &ix->scores, &ix->lists_s, &ix->lists_i,
+                      &ix->overflow, &ix->h_xq, &ix->h_D, &ix->h_I})
         b->release();
+    for (auto& W : ix->bws)
+        for (DevBuf* b : {&W.xq_f32, &W.xq_bf16, &W.xnorm2, &W.eps, &W.thr, &W.counts, &W.cand_s, &W.cand_i}) b->release();
+    for (int w = 0; w < 2; ++w) {
+        if (ix->aux[w]) {
+            cudaStreamSynchronize(ix->aux[w]);
+            cudaStreamDestroy(ix->aux[w]);
+        }
+        if (ix->ev_join[w]) cudaEventDestroy(ix->ev_join[w]);
+    }
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
     if (ix->xb_f32) cudaFree(ix->xb_f32);
     if (ix->xb_bf16) cudaFree(ix->xb_bf16);
     if (ix->ynorm2) cudaFree(ix->ynorm2);
@@ -586,6 +639,8 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "profile") ix->profile = value != 0;
     else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
     else if (n == "l2_hints") ix->l2_hints = value != 0;
+    else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = value != 0;
+    else if (n == "streams" && (value == 1 || value == 2)) ix->streams = int(value);
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
     else {
