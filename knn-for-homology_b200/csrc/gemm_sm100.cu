@@ -350,8 +350,32 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
-            if (args.debug_skip_epilogue) {
+            if (args.debug_skip_epilogue == 1) {
                 // measurement aid: main loop only
+            } else if (args.debug_skip_epilogue == 2) {
+                // measurement aid: TMEM reads only
+                uint32_t sink = 0;
+#pragma unroll 1
+                for (int cg = 0; cg < BN / 32; ++cg) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + uint32_t(cg * 32), r);
+                    tmem_ld_wait();
+                    sink ^= r[0] ^ r[31];
+                }
+                if (sink == 0x7fc12345u) args.counts[0] = 1;
+            } else if (args.debug_skip_epilogue == 3) {
+                // measurement aid: TMEM reads + threshold compares, survivors ignored
+                uint32_t flagged = 0;
+#pragma unroll 1
+                for (int cg = 0; cg < BN / 32; ++cg) {
+                    float v[32];
+                    load_scores<L2>(taddr + uint32_t(cg * 32), jbase + cg * 32, args, v);
+                    bool any = false;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) any |= (v[i] >= thr);
+                    if (__any_sync(0xffffffffu, any)) flagged |= 1u << cg;
+                }
+                if (flagged == 0xdeadbeefu) args.counts[0] = 1;
             } else if constexpr (DENSE) {
 #pragma unroll 1
                 for (int cg = 0; cg < BN / 32; ++cg) {

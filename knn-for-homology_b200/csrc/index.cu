@@ -639,7 +639,7 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "profile") ix->profile = value != 0;
     else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
     else if (n == "l2_hints") ix->l2_hints = value != 0;
-    else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = value != 0;
+    else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);
     else if (n == "streams" && (value == 1 || value == 2)) ix->streams = int(value);
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
