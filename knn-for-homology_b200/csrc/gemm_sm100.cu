@@ -42,7 +42,8 @@ struct Cfg {
     static constexpr uint32_t kBytesA = BM * BK * 2;
     static constexpr uint32_t kBytesB = kRowsB * BK * 2;
     static constexpr uint32_t kBytesStage = kBytesA + kBytesB;
-    static constexpr size_t kSmemBytes = size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr size_t kSmemBytes =
+        size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 512 * 8 /*survivor stash*/;
     // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
     // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 (M = 256 for a CTA pair).
     static constexpr uint32_t kInstrDesc =
@@ -229,6 +230,35 @@ struct GemmArgs {
     int debug_skip_epilogue;   // experiments only: accumulators are not read (results are then meaningless)
 };
 
+constexpr int kStashEntries = 512;  // per epilogue warp: (score bits, lane << 8 | column in tile)
+
+// Appends the stashed survivors of one warp to the per-query candidate lists.  Four entries per lane
+// are in flight so that the atomics' round trips overlap.
+__device__ __forceinline__ void drain_stash(const uint2* stash, int n, int lane, int64_t q_warp0, int64_t jbase,
+                                            const GemmArgs& args) {
+    for (int e0 = 0; e0 < n; e0 += 128) {
+        uint2 ent[4];
+        int pos[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 32 + lane;
+            pos[u] = -1;
+            if (e < n) {
+                ent[u] = stash[e];
+                pos[u] = atomicAdd(args.counts + (q_warp0 + (ent[u].y >> 8)), 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (pos[u] >= 0 && pos[u] < args.cap) {
+                const int64_t q = q_warp0 + (ent[u].y >> 8);
+                args.cand_scores[q * int64_t(args.cap) + pos[u]] = __uint_as_float(ent[u].x);
+                args.cand_ids[q * int64_t(args.cap) + pos[u]] = uint32_t(jbase + (ent[u].y & 255u));
+            }
+        }
+    }
+}
+
 template <bool L2>
 __device__ __forceinline__ void load_scores(uint32_t taddr, int64_t j_first, const GemmArgs& args, float (&v)[32]) {
     uint32_t r[32];
@@ -340,6 +370,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint2* stash = reinterpret_cast<uint2*>(smem + size_t(C::kStages) * C::kBytesStage + 256) + (warp - 2) * kStashEntries;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        int nst = 0;  // warp-uniform number of stashed survivors
         for (int tile = unit; tile < num_tiles; tile += num_units) {
             const int mt = tile % args.m_tiles;
             const int nt = tile / args.m_tiles;
@@ -350,6 +383,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
+            const int64_t q_warp0 = q - lane;  // query of lane 0 of this warp
             if (args.debug_skip_epilogue == 1) {
                 // measurement aid: main loop only
             } else if (args.debug_skip_epilogue == 2) {
@@ -405,10 +439,10 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     __syncwarp();  // reconverge before the next warp-wide tcgen05.ld
                 }
             } else {
-                // Pass A: one compare per score; count this query's survivors in the tile.  Survivors are
-                // rare once the threshold has tightened, so the common path is LDTM + 32 FSETP per group.
-                int cnt = 0;
-                uint32_t flagged = 0;  // warp-uniform: column groups in which some lane has a survivor
+                // One compare per score.  Survivors (rare once the threshold has tightened) are parked in a
+                // small per-warp shared-memory stash so that the TMEM stage can be handed back to the MMA
+                // issuer right away; the global atomics and stores that append them to the candidate lists
+                // run after the release, under the next tile's MMAs (their latency is off the critical path).
 #pragma unroll 1
                 for (int cg = 0; cg < BN / 32; ++cg) {
                     float v[32];
@@ -417,44 +451,27 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     bool any = false;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) any |= (v[i] >= thr);
-                    if (__any_sync(0xffffffffu, any)) {
-                        flagged |= 1u << cg;
-                        if (any) {
-                            if (j_first + 32 <= args.j1) {
+                    if (__any_sync(0xffffffffu, any)) {  // warp-uniform
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) cnt += (v[i] >= thr) ? 1 : 0;
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) cnt += (v[i] >= thr && j_first + i < args.j1) ? 1 : 0;
+                        for (int i0 = 0; i0 < 32; i0 += 8) {
+                            if (nst + 8 * 32 > kStashEntries) {  // rare (dense early panels): make room
+                                __syncwarp();
+                                drain_stash(stash, nst, lane, q_warp0, jbase, args);
+                                __syncwarp();
+                                nst = 0;
                             }
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (flagged) {  // warp-uniform
-                    // one reservation per query and tile (all lanes' atomics are in flight together), then
-                    // Pass B re-reads the flagged groups from TMEM and stores the survivors
-                    int pos = 0;
-                    if (cnt > 0) pos = atomicAdd(args.counts + q, cnt);
-                    float* cs = args.cand_scores + q * int64_t(args.cap);
-                    uint32_t* ci = args.cand_ids + q * int64_t(args.cap);
-                    while (flagged) {
-                        const int cg = __ffs(int(flagged)) - 1;
-                        flagged &= flagged - 1;
-                        float v[32];
-                        load_scores<L2>(taddr + uint32_t(cg * 32), jbase + cg * 32, args, v);
-                        const int64_t j_first = jbase + cg * 32;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (v[i] >= thr && j_first + i < args.j1) {
-                                if (pos < args.cap) {
-                                    cs[pos] = v[i];
-                                    ci[pos] = uint32_t(j_first + i);
+                            for (int i = i0; i < i0 + 8; ++i) {
+                                const bool hit = (v[i] >= thr) && (j_first + i < args.j1);
+                                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                                if (m) {  // warp-uniform
+                                    if (hit)
+                                        stash[nst + __popc(m & lt_mask)] =
+                                            make_uint2(__float_as_uint(v[i]), (uint32_t(lane) << 8) | uint32_t(cg * 32 + i));
+                                    nst += __popc(m);
                                 }
-                                ++pos;
                             }
                         }
-                        __syncwarp();
                     }
                 }
             }
@@ -465,6 +482,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 // tile has drained it; the MMA issuer waits on the leader's barrier
                 if constexpr (CG == 1) mbar_arrive(&bars->acc_empty[acc]);
                 else mbar_arrive_remote(&bars->acc_empty[acc], 0);
+            }
+            if (nst) {  // warp-uniform
+                __syncwarp();
+                drain_stash(stash, nst, lane, q_warp0, jbase, args);
+                __syncwarp();
+                nst = 0;
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }

@@ -1,0 +1,122 @@
+"""The reference drivers' call sequences, restated on top of the `faiss` alias package, against
+the oracle (GPU).  The drivers themselves are Python glue above the boundary and are not rebuilt;
+these tests show that they would run unchanged: same calls, same argument meaning, same outputs
+on disk.  (The unmodified drivers were run against the oracle in tests/golden/make_golden.py.)"""
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from oracle import flat_oracle as fo
+from oracle.parity import check_parity
+
+
+def test_alias_satisfies_reference_imports():
+    """CPU: what the reference touches at import time (seqvec_search/main.py:9,23)."""
+    import faiss
+
+    assert faiss.IndexLSH is not None  # evaluated in a type annotation at import
+    assert callable(faiss.normalize_L2) and callable(faiss.IndexFlat)
+
+
+@pytest.mark.gpu
+def test_cath_search_and_save_flow(tmp_path):
+    """cath/search.py:29-53: every *.npy in a directory (any width, fp16 allowed), both metrics,
+    hits+1 search, self hit dropped, results written as npz."""
+    import faiss
+
+    rng = np.random.default_rng(0)
+    mats = {"aac": rng.random((400, 20)).astype(np.float32),          # amino-acid composition width
+            "prott5_half": rng.standard_normal((300, 1024)).astype(np.float16),  # fp16 file, up-cast at :40
+            "esm": rng.standard_normal((257, 1280)).astype(np.float32),
+            "unirep": rng.standard_normal((130, 1900)).astype(np.float32)}
+    for name, m in mats.items():
+        np.save(tmp_path / f"{name}.npy", m)
+
+    def search(embeddings, hits=10, metric=faiss.METRIC_INNER_PRODUCT):  # cath/search.py:13-26
+        if metric == faiss.METRIC_INNER_PRODUCT:
+            embeddings = embeddings.copy()
+            faiss.normalize_L2(embeddings)
+        index = faiss.IndexFlat(embeddings.shape[1], metric)
+        index.add(embeddings)
+        scores, results = index.search(embeddings, hits + 1)
+        return results[:, 1:], scores[:, 1:]
+
+    for mname, metric in [("Cosine", faiss.METRIC_INNER_PRODUCT), ("Euclidean", faiss.METRIC_L2)]:
+        hits, scores = {}, {}
+        for file_path in sorted(tmp_path.glob("*.npy")):
+            embeddings = np.load(file_path).astype(np.float32)
+            start = time.time()
+            hits[file_path.stem], scores[file_path.stem] = search(embeddings, metric=metric)
+            tmp_path.joinpath(file_path.with_suffix(f".{mname.lower()}-search-time.txt")).write_text(str(time.time() - start))
+        np.savez(tmp_path / f"hits_{mname.lower()}.npz", **hits)
+        np.savez(tmp_path / f"scores_{mname.lower()}.npz", **scores)
+        back = np.load(tmp_path / f"hits_{mname.lower()}.npz")
+        for name, m in mats.items():
+            x = m.astype(np.float32)
+            if metric == fo.METRIC_INNER_PRODUCT:
+                fo.normalize_L2(x)
+            D_ref, I_ref = fo.knn_flat(x, x, 11, metric)
+            check_parity(np.ascontiguousarray(scores[name]), np.ascontiguousarray(back[name]),
+                         np.ascontiguousarray(D_ref[:, 1:]), np.ascontiguousarray(I_ref[:, 1:]), x, x, metric,
+                         max_excused_frac=1e-2)
+
+
+@pytest.mark.gpu
+def test_pfam_proteins_search_flat_flow(tmp_path):
+    """pfam/proteins_search.py:17-57, mode 'flat': normalise in place, IndexFlat IP, train, add,
+    write_index, all-vs-all k=1000, save scores/hits; consumer expects column 0 = self
+    (pfam/proteins.py:85-122)."""
+    import faiss
+
+    rng = np.random.default_rng(1)
+    centers = rng.standard_normal((40, 1024)).astype(np.float32)
+    emb = (centers[rng.integers(0, 40, 9000)] + 0.35 * rng.standard_normal((9000, 1024))).astype(np.float32)
+    np.save(tmp_path / "full_sequences.npy", emb.astype(np.float16))
+
+    embeddings = np.load(tmp_path / "full_sequences.npy").astype(np.float32)
+    faiss.normalize_L2(embeddings)
+    index = faiss.IndexFlat(embeddings.shape[1], faiss.METRIC_INNER_PRODUCT)
+    index.train(embeddings)
+    index.add(embeddings)
+    index_file = tmp_path / "full_sequences_flat.index"
+    faiss.write_index(index, str(index_file))
+    assert index_file.stat().st_size == 45 + embeddings.nbytes  # what the driver prints as "Index: ..."
+    flat_scores, flat_hits = index.search(embeddings, 1000)
+    np.save(tmp_path / "full_sequences_flat_scores.npy", flat_scores)
+    np.save(tmp_path / "full_sequences_flat_hits.npy", flat_hits)
+
+    hits = np.load(tmp_path / "full_sequences_flat_hits.npy")
+    assert hits.shape == (9000, 1000) and hits.dtype == np.int64
+    assert np.array_equal(hits[:, 0], np.arange(9000))  # remove_self_hit finds nothing to fix
+    x = np.load(tmp_path / "full_sequences.npy").astype(np.float32)
+    fo.normalize_L2(x)
+    sample = np.arange(0, 9000, 45)
+    D_ref, I_ref = fo.knn_flat(x[sample], x, 1000, fo.METRIC_INNER_PRODUCT)
+    check_parity(flat_scores[sample], hits[sample], D_ref, I_ref, x[sample], x, fo.METRIC_INNER_PRODUCT,
+                 max_excused_frac=5e-3)
+    # main.py:131-132: a pre-built index can be read back and searched
+    again = faiss.read_index(str(index_file))
+    D2, I2 = again.search(embeddings[:64], 13)
+    assert np.array_equal(I2, hits[:64, :13])
+
+
+@pytest.mark.gpu
+def test_faiss_search_flow_mutates_inputs_like_the_reference(golden_dir):
+    """seqvec_search/main.py:29-50 normalises queries and haystack IN PLACE; callers see it."""
+    import faiss
+
+    queries = np.load(golden_dir / "pfam-20-dist/test.npy")
+    haystack = np.load(golden_dir / "pfam-20-dist/train.npy")
+    q0 = queries.copy()
+    faiss.normalize_L2(queries)
+    faiss.normalize_L2(haystack)
+    assert not np.array_equal(q0, queries)
+    np.testing.assert_allclose(np.linalg.norm(queries, axis=1), 1.0, atol=1e-5)
+    index = faiss.IndexFlat(haystack.shape[1], faiss.METRIC_INNER_PRODUCT)
+    index.train(haystack)
+    index.add(haystack)
+    scores, result = index.search(queries, 13)
+    D_ref, I_ref = fo.knn_flat(queries, haystack, 13, 0)
+    check_parity(scores, result, D_ref, I_ref, queries, haystack, 0)
