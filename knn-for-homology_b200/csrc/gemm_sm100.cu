@@ -48,7 +48,7 @@ struct Cfg {
     static constexpr uint32_t kBytesB = kRowsB * BK * 2;
     static constexpr uint32_t kBytesStage = kBytesA + kBytesB;
     static constexpr size_t kSmemBytes =
-        size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 512 * 8 /*survivor stash*/;
+        size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (512 * 8 + 8 * 32 * 16) + 16 /*EpilogueSmem*/;
     // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
     // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 (M = 256 for a CTA pair).
     static constexpr uint32_t kInstrDesc =
@@ -119,7 +119,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     uint32_t raddr;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -237,6 +237,12 @@ struct GemmArgs {
 
 constexpr int kStashEntries = 512;  // per epilogue warp: (score bits, lane << 8 | column in tile)
 
+struct EpilogueSmem {                 // one slice per epilogue warp
+    uint2 stash[4][kStashEntries];    // survivors waiting to be appended to the global candidate lists
+    float4 dump[4][8 * 32];           // the 32 scores of every lane of a flagged column group ([j/4][lane])
+    int count[4];                     // entries in the stash (may run past kStashEntries: overflow went direct)
+};
+
 // Appends the stashed survivors of one warp to the per-query candidate lists.  Four entries per lane
 // are in flight so that the atomics' round trips overlap.
 __device__ __forceinline__ void drain_stash(const uint2* stash, int n, int lane, int64_t q_warp0, int64_t jbase,
@@ -264,6 +270,15 @@ __device__ __forceinline__ void drain_stash(const uint2* stash, int n, int lane,
     }
 }
 
+__device__ __forceinline__ void append_direct(uint2 ent, int64_t q_warp0, int64_t jbase, const GemmArgs& args) {
+    const int64_t q = q_warp0 + (ent.y >> 8);
+    const int pos = atomicAdd(args.counts + q, 1);
+    if (pos < args.cap) {
+        args.cand_scores[q * int64_t(args.cap) + pos] = __uint_as_float(ent.x);
+        args.cand_ids[q * int64_t(args.cap) + pos] = uint32_t(jbase + (ent.y & 255u));
+    }
+}
+
 template <bool L2>
 __device__ __forceinline__ void load_scores(uint32_t taddr, int64_t j_first, const GemmArgs& args, float (&v)[32]) {
     uint32_t r[32];
@@ -284,7 +299,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment for the 128B-swizzle atoms; plain pointer arithmetic keeps the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     Barriers* bars = reinterpret_cast<Barriers*>(smem + size_t(C::kStages) * C::kBytesStage);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -375,9 +391,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint2* stash = reinterpret_cast<uint2*>(smem + size_t(C::kStages) * C::kBytesStage + 256) + warp * kStashEntries;
-        const unsigned lt_mask = (1u << lane) - 1u;
-        int nst = 0;  // warp-uniform number of stashed survivors
+        EpilogueSmem* es = reinterpret_cast<EpilogueSmem*>(smem + size_t(C::kStages) * C::kBytesStage + 256);
+        uint2* stash = es->stash[warp];
+        float4* dump = es->dump[warp];
+        int* stash_count = &es->count[warp];
+        if (lane == 0) *stash_count = 0;
+        __syncwarp();
         for (int tile = unit; tile < num_tiles; tile += num_units) {
             const int mt = tile % args.m_tiles;
             const int nt = tile / args.m_tiles;
@@ -444,39 +463,40 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     __syncwarp();  // reconverge before the next warp-wide tcgen05.ld
                 }
             } else {
-                // One compare per score.  Survivors (rare once the threshold has tightened) are parked in a
-                // small per-warp shared-memory stash so that the TMEM stage can be handed back to the MMA
-                // issuer right away; the global atomics and stores that append them to the candidate lists
-                // run after the release, under the next tile's MMAs (their latency is off the critical path).
+                // One compare per score (LDTM + 16 FMNMX3 + FSETP + vote per 32 columns).  A column group in
+                // which some lane has a survivor (rare once the threshold has tightened) takes the side path:
+                // the lanes' scores are dumped to shared memory, each lane builds its 32-bit survivor mask and
+                // walks its set bits, parking (score, lane, column) in the warp's stash.  The stash is appended
+                // to the global candidate lists only after the TMEM stage has been handed back to the MMA
+                // issuer, so atomics and stores run under the next tile's MMAs.
 #pragma unroll 1
                 for (int cg = 0; cg < BN / 32; ++cg) {
                     float v[32];
                     load_scores<L2>(taddr + uint32_t(cg * 32), jbase + cg * 32, args, v);
-                    const int64_t j_first = jbase + cg * 32;
                     bool any = false;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) any |= (v[i] >= thr);
                     if (__any_sync(0xffffffffu, any)) {  // warp-uniform
 #pragma unroll
-                        for (int i0 = 0; i0 < 32; i0 += 8) {
-                            if (nst + 8 * 32 > kStashEntries) {  // rare (dense early panels): make room
-                                __syncwarp();
-                                drain_stash(stash, nst, lane, q_warp0, jbase, args);
-                                __syncwarp();
-                                nst = 0;
-                            }
+                        for (int t = 0; t < 8; ++t)
+                            dump[t * 32 + lane] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                        uint32_t mask = 0;
+                        if (any) {
 #pragma unroll
-                            for (int i = i0; i < i0 + 8; ++i) {
-                                const bool hit = (v[i] >= thr) && (j_first + i < args.j1);
-                                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                                if (m) {  // warp-uniform
-                                    if (hit)
-                                        stash[nst + __popc(m & lt_mask)] =
-                                            make_uint2(__float_as_uint(v[i]), (uint32_t(lane) << 8) | uint32_t(cg * 32 + i));
-                                    nst += __popc(m);
-                                }
-                            }
+                            for (int i = 0; i < 32; ++i) mask |= (v[i] >= thr) ? (1u << i) : 0u;
+                            const int64_t left = args.j1 - (jbase + cg * 32);  // columns of this group inside the panel
+                            if (left < 32) mask &= left <= 0 ? 0u : ((1u << int(left)) - 1u);
                         }
+                        while (mask) {  // a lane reads back only what it dumped itself
+                            const int i = __ffs(int(mask)) - 1;
+                            mask &= mask - 1;
+                            const float val = reinterpret_cast<const float*>(dump + (i >> 2) * 32 + lane)[i & 3];
+                            const uint2 ent = make_uint2(__float_as_uint(val), (uint32_t(lane) << 8) | uint32_t(cg * 32 + i));
+                            const int slot = atomicAdd(stash_count, 1);
+                            if (slot < kStashEntries) stash[slot] = ent;
+                            else append_direct(ent, q_warp0, jbase, args);  // stash full (dense early panels)
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -488,11 +508,15 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 if constexpr (CG == 1) mbar_arrive(&bars->acc_empty[acc]);
                 else mbar_arrive_remote(&bars->acc_empty[acc], 0);
             }
-            if (nst) {  // warp-uniform
+            {
                 __syncwarp();
-                drain_stash(stash, nst, lane, q_warp0, jbase, args);
-                __syncwarp();
-                nst = 0;
+                int nst = *stash_count;  // same value in every lane
+                if (nst) {
+                    nst = nst < kStashEntries ? nst : kStashEntries;
+                    drain_stash(stash, nst, lane, q_warp0, jbase, args);
+                    __syncwarp();
+                    if (lane == 0) *stash_count = 0;
+                }
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
