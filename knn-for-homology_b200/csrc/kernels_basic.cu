@@ -257,19 +257,33 @@ rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, in
             if (lane == 0) ci[i] = kInvalidId;
             continue;
         }
+        // 8 independent 16-byte loads per lane are issued before the FMAs that consume them (a 1024-d row
+        // is exactly one such round); the FMA order is the scan kernel's, so the bits are too.
         float a = 0.f;
-        for (int c = lane; c < dp4; c += 32) {
-            float4 y;
-            if (BF16DB) {
-                uint2 p = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xb) + int64_t(id) * dp)[c];
-                float2 u = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.x));
-                float2 v = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.y));
-                y = make_float4(u.x, u.y, v.x, v.y);
-            } else {
-                y = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xb) + int64_t(id) * dp) + c);
+        for (int c0 = lane; c0 < dp4; c0 += 8 * 32) {
+            float4 y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32;
+                if (c < dp4) {
+                    if (BF16DB) {
+                        uint2 p = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xb) + int64_t(id) * dp)[c];
+                        float2 lo = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.x));
+                        float2 hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.y));
+                        y[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    } else {
+                        y[u] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xb) + int64_t(id) * dp) + c);
+                    }
+                }
             }
-            const float4 qv = sq[c];
-            a = fmaf(y.x, qv.x, a); a = fmaf(y.y, qv.y, a); a = fmaf(y.z, qv.z, a); a = fmaf(y.w, qv.w, a);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32;
+                if (c < dp4) {
+                    const float4 qv = sq[c];
+                    a = fmaf(y[u].x, qv.x, a); a = fmaf(y[u].y, qv.y, a); a = fmaf(y[u].z, qv.z, a); a = fmaf(y[u].w, qv.w, a);
+                }
+            }
         }
         a = warp_sum(a);
         if (lane == 0) {

@@ -335,6 +335,99 @@ tighten_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __restr
     if (tid == 0) counts[q] = sm.base;
 }
 
+
+// Warp-per-query variant for small k (candidate lists of a few hundred entries): the keys live in
+// registers and the k-th largest is found by a bit-by-bit search (32 rounds of compare + warp
+// reduce) - no block-wide barriers, 8 queries per CTA.
+template <int MAXE>
+__device__ __forceinline__ uint32_t warp_kth_largest_reg(const float* __restrict__ cs, int cnt, int k, int lane) {
+    uint32_t keys[MAXE];
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        const int i = e * 32 + lane;
+        const float s = i < cnt ? cs[i] : 0.f;
+        keys[e] = (i < cnt && s == s) ? orderable_f32(s) : 0u;
+    }
+    uint32_t t = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = t | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) c += keys[e] >= cand ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) t = cand;  // at least k keys are >= cand: the k-th largest has this bit pattern so far
+    }
+    return t;
+}
+
+__device__ __forceinline__ uint32_t warp_kth_largest_mem(const float* __restrict__ cs, int cnt, int k, int lane) {
+    uint32_t t = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = t | (1u << bit);
+        int c = 0;
+        for (int i = lane; i < cnt; i += 32) {
+            const float s = cs[i];
+            c += (s == s && orderable_f32(s) >= cand) ? 1 : 0;
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) t = cand;
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __restrict__ cand_scores,
+                    uint32_t* __restrict__ cand_ids, int cap, const float* __restrict__ eps, int64_t nq, int k,
+                    int* __restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    int cnt = counts[q];
+    if (cnt > cap) {
+        if (lane == 0) atomicExch(overflow, 1);
+        cnt = cap;
+    }
+    if (cnt < k || cnt == 0) return;  // fewer than k candidates seen: everything stays a candidate
+    float* cs = cand_scores + q * int64_t(cap);
+    uint32_t* ci = cand_ids + q * int64_t(cap);
+    uint32_t kth;
+    if (cnt <= 16 * 32) kth = warp_kth_largest_reg<16>(cs, cnt, k, lane);
+    else if (cnt <= 32 * 32) kth = warp_kth_largest_reg<32>(cs, cnt, k, lane);
+    else kth = warp_kth_largest_mem(cs, cnt, k, lane);
+    float t = from_orderable_f32(kth) - 2.0f * eps[q];
+    if (!(t == t)) t = -FLT_MAX;
+    const float old = thr[q];
+    if (old > t) t = old;
+    // ordered in-place compaction, 32 entries at a time (a chunk is read completely before it is written,
+    // and writes land at or before positions that were already read)
+    int base = 0;
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        const int i = c0 + lane;
+        float s = 0.f;
+        uint32_t id = kInvalidId;
+        bool keep = false;
+        if (i < cnt) {
+            s = cs[i];
+            id = ci[i];
+            keep = (s >= t) && id != kInvalidId;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int p = base + __popc(ballot & ((1u << lane) - 1u));
+            cs[p] = s;
+            ci[p] = id;
+        }
+        base += __popc(ballot);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        thr[q] = t;
+        counts[q] = base;
+    }
+}
+
 __global__ void init_filter_kernel(float* thr, int* counts, int64_t nq, int64_t nq_pad, int first_count) {
     const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q >= nq_pad) return;
@@ -383,8 +476,13 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
                    cudaStream_t s) {
     (void)tau_out;
     if (nq <= 0) return KNN_OK;
-    tighten_kernel<<<unsigned(nq), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap, eps, k,
-                                                compact, overflow);
+    if (k <= 256 && compact) {
+        tighten_warp_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap,
+                                                                   eps, nq, k, overflow);
+    } else {
+        tighten_kernel<<<unsigned(nq), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap, eps, k,
+                                                    compact, overflow);
+    }
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }
