@@ -86,6 +86,17 @@ int knn_index_search(knn_index* idx, int64_t nq, const float* xq, int64_t k, flo
 int knn_index_search_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, float* D_dev,
                          int64_t* I_dev, int64_t id_base, void* stream);
 
+/* Two-phase search for a row-sharded database (new).  Phase 1 runs the
+ * tensor-core filter over this shard and writes lower_dev[q], a lower bound of the TRUE k-th best score
+ * of query q within the shard (-FLT_MAX when the shard cannot offer one).  The caller combines the
+ * bounds of all shards (element-wise MAX, e.g. an NCCL all-reduce) and passes the result to phase 2,
+ * which rescores only the candidates that can still be in the global top-k and returns this shard's
+ * (D, I).  At most 131072 queries per call; filter and finish must be called in pairs with the same
+ * nq, xq_dev and k.  Scores are comparable across shards for both metrics. */
+int knn_index_search_filter_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, float* lower_dev, void* stream);
+int knn_index_search_finish_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, const float* lower_dev,
+                                float* D_dev, int64_t* I_dev, int64_t id_base, void* stream);
+
 /* Copy rows [i0, i0+n) back to the host as float32 (faiss Index::reconstruct_n); feeds
  * write_index (pfam/proteins_search.py:39-40). */
 int knn_index_reconstruct(knn_index* idx, int64_t i0, int64_t n, float* out);
@@ -97,9 +108,9 @@ int knn_merge_topk_dev(int metric, int64_t nq, int64_t k, int nlists, const floa
                        const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev, void* stream);
 
 /* Tuning / introspection.  Parameters: "path" (0 auto, 1 exact fp32 scan, 2 tensor-core
- * filter + rerank), "query_batch", "profile" (1: time the dominant kernel with CUDA events).
- * Statistics of the last search: "path", "launches", "gemm_launches", "gemm_ms",
- * "candidates", "overflow_batches", "rerank_pairs". */
+ * filter + rerank), "query_batch", "profile" (1: time the dominant kernel with CUDA events),
+ * "cta_group" (tcgen05 cta_group of the GEMM kernel, 1 or 2), "tensor_min_nq", "tensor_min_n".
+ * Statistics of the last search: "path", "launches", "gemm_launches", "gemm_ms", "overflow_batches". */
 int knn_index_set_param(knn_index* idx, const char* name, int64_t value);
 int knn_index_get_stat(const knn_index* idx, const char* name, double* out);
 

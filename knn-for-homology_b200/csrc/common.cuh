@@ -147,5 +147,9 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
                    int* overflow, cudaStream_t s);
 // thr <- -FLT_MAX (real queries) / +FLT_MAX (padding rows); counts <- first_count / 0.
 int launch_init_filter(FilterState st, int64_t nq, int64_t nq_pad, int first_count, cudaStream_t s);
+// Two-phase (sharded) search: lower[q] = thr + eps on the way out; thr <- max(thr, lower - eps) on the way in.
+int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* lower, cudaStream_t s);
+int launch_apply_lower(float* thr, const float* eps, const float* lower, int64_t nq, cudaStream_t s);
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
 
 }  // namespace knn

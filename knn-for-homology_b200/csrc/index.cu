@@ -92,13 +92,17 @@ struct knn_index {
     // workspaces: exact path / staging
     DevBuf stage, xq_f32, xnorm2, eps, scores, lists_s, lists_i, overflow;
     DevBuf h_xq, h_D, h_I;
-    // tensor path: two query batches are in flight on two streams (the CUDA-core kernels of one
-    // batch - tighten, rerank, select - run under the tensor-core GEMM of the other)
-    struct BatchWs {
+    // tensor path: per-query state of the filter (queries, thresholds, candidate lists)
+    struct TensorWs {
         DevBuf xq_f32, xq_bf16, xnorm2, eps, thr, counts, cand_s, cand_i;
-    } bws[2];
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    };
+    TensorWs ws1;  // one query batch (single-call search)
+    TensorWs ws2;  // all queries of a two-phase search (filter ... exchange ... finish)
+    struct Pending {
+        bool active = false, tensor = false;
+        int64_t nq = 0, qb = 0, nbatches = 0;
+        int k = 0, cap = 0;
+    } pend;
     // parameters
     int path_param = 0;
     int64_t query_batch = 16384;
@@ -106,7 +110,6 @@ struct knn_index {
     int64_t tensor_min_nq = 64, tensor_min_n = 8192;
     int cta_group = 2;
     int l2_hints = 0;
-    int streams = 2;
     int debug_skip_epilogue = 0;
     // statistics of the last search
     int last_path = 0;
@@ -211,106 +214,100 @@ int search_exact(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D
 }
 
 // ---- tensor path --------------------------------------------------------------------------
-int ensure_aux(knn_index* ix) {
-    if (ix->aux[0]) return KNN_OK;
-    for (int i = 0; i < 2; ++i) {
-        KNN_CHECK_CUDA(cudaStreamCreateWithFlags(&ix->aux[i], cudaStreamNonBlocking));
-        KNN_CHECK_CUDA(cudaEventCreateWithFlags(&ix->ev_join[i], cudaEventDisableTiming));
-    }
-    KNN_CHECK_CUDA(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
+int candidate_capacity(int k) {
+    int cap = 8192;
+    while (cap < 8 * k) cap *= 2;
+    return cap;
+}
+
+int tensor_ws_ensure(knn_index::TensorWs& W, int64_t rows, int dp, int cap) {
+    KNN_CHECK(W.xq_f32.ensure(size_t(rows) * dp * sizeof(float)));
+    KNN_CHECK(W.xq_bf16.ensure(size_t(rows) * dp * sizeof(__nv_bfloat16)));
+    KNN_CHECK(W.xnorm2.ensure(size_t(rows) * sizeof(float)));
+    KNN_CHECK(W.eps.ensure(size_t(rows) * sizeof(float)));
+    KNN_CHECK(W.thr.ensure(size_t(rows) * sizeof(float)));
+    KNN_CHECK(W.counts.ensure(size_t(rows) * sizeof(int)));
+    KNN_CHECK(W.cand_s.ensure(size_t(rows) * cap * sizeof(float)));
+    KNN_CHECK(W.cand_i.ensure(size_t(rows) * cap * sizeof(uint32_t)));
     return KNN_OK;
 }
 
-int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
-                  cudaStream_t s) {
-    const int largest = ix->metric == KNN_METRIC_INNER_PRODUCT;
-    const int64_t N = ix->ntotal;
-    int cap = 8192;
-    while (cap < 8 * k) cap *= 2;
-    const int64_t first_panel = N < cap / 2 ? N : cap / 2;
-    int64_t qb = ix->query_batch;
-    if (qb > nq) qb = nq;
-    qb = round_up(qb, 256);
-    const int64_t nbatches = (nq + qb - 1) / qb;
-    // event timing of the GEMM launches needs them serialised: profile mode uses one stream
-    const int nstreams = (ix->streams >= 2 && nbatches >= 2 && !ix->profile) ? 2 : 1;
-    for (int w = 0; w < nstreams; ++w) {
-        auto& W = ix->bws[w];
-        KNN_CHECK(W.xq_f32.ensure(size_t(qb) * ix->dp * sizeof(float)));
-        KNN_CHECK(W.xq_bf16.ensure(size_t(qb) * ix->dp * sizeof(__nv_bfloat16)));
-        KNN_CHECK(W.xnorm2.ensure(size_t(qb) * sizeof(float)));
-        KNN_CHECK(W.eps.ensure(size_t(qb) * sizeof(float)));
-        KNN_CHECK(W.thr.ensure(size_t(qb) * sizeof(float)));
-        KNN_CHECK(W.counts.ensure(size_t(qb) * sizeof(int)));
-        KNN_CHECK(W.cand_s.ensure(size_t(qb) * cap * sizeof(float)));
-        KNN_CHECK(W.cand_i.ensure(size_t(qb) * cap * sizeof(uint32_t)));
-    }
-    KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(nbatches)));
-    int* d_overflow = ix->overflow.as<int>();
+FilterState filter_state(knn_index::TensorWs& W, int64_t off, int cap) {
+    FilterState st;
+    st.thr = W.thr.as<float>() + off;
+    st.counts = W.counts.as<int>() + off;
+    st.cand_scores = W.cand_s.as<float>() + off * cap;
+    st.cand_ids = W.cand_i.as<uint32_t>() + off * cap;
+    st.cap = cap;
+    return st;
+}
+
+int tensor_prepare(knn_index* ix) {
     if (!ix->plan) KNN_CHECK(gemm_plan_create(&ix->plan, ix->device));
     gemm_plan_set_cta_group(ix->plan, ix->cta_group);
     gemm_plan_set_l2_hints(ix->plan, ix->l2_hints);
     gemm_plan_set_debug(ix->plan, ix->debug_skip_epilogue);
-    KNN_CHECK_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int) * size_t(nbatches), s));
-    if (nstreams == 2) {
-        KNN_CHECK(ensure_aux(ix));
-        KNN_CHECK_CUDA(cudaEventRecord(ix->ev_fork, s));
-        for (int w = 0; w < 2; ++w) KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->aux[w], ix->ev_fork, 0));
-    }
+    return KNN_OK;
+}
 
-    for (int64_t b = 0; b < nbatches; ++b) {
-        const int64_t q0 = b * qb;
-        const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
-        const int64_t nb_pad = round_up(nb, 256);
-        const int w = nstreams == 2 ? int(b & 1) : 0;
-        cudaStream_t st_ = nstreams == 2 ? ix->aux[w] : s;
-        auto& W = ix->bws[w];
-        FilterState st;
-        st.thr = W.thr.as<float>();
-        st.counts = W.counts.as<int>();
-        st.cand_scores = W.cand_s.as<float>();
-        st.cand_ids = W.cand_i.as<uint32_t>();
-        st.cap = cap;
-        KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb_pad, ix->d, ix->dp, W.xq_f32.as<float>(),
-                                      W.xq_bf16.as<__nv_bfloat16>(), W.xnorm2.as<float>(), W.eps.as<float>(), ix->stats,
-                                      ix->metric, st_));
-        KNN_CHECK(launch_init_filter(st, nb, nb_pad, int(first_panel), st_));
-        int64_t j0 = 0;
-        bool first = true;
-        while (j0 < N) {
-            int64_t len = first ? first_panel : j0;  // processed rows double with every panel
-            int64_t j1 = j0 + len < N ? j0 + len : N;
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (ix->profile) {
-                e0 = next_event(ix);
-                e1 = next_event(ix);
-                cudaEventRecord(e0, st_);
-            }
-            KNN_CHECK(gemm_filter_launch(ix->plan, W.xq_bf16.as<__nv_bfloat16>(), nb, nb_pad, ix->dp, ix->xb_bf16, N,
-                                         ix->ynorm2, j0, j1, ix->metric, first, st, st_));
-            if (ix->profile) cudaEventRecord(e1, st_);
-            ix->st_gemm_launches++;
-            KNN_CHECK(launch_tighten(st, W.eps.as<float>(), nb, k, 1, nullptr, d_overflow + b, st_));
-            j0 = j1;
-            first = false;
+// Filter phase of one query batch (rows [off, off+nb) of W): tensor-core scores over database panels of
+// growing size, survivors appended to the candidate lists, thresholds tightened after every panel.
+// On return thr[q] = (k-th best approximate score) - 2 eps[q].
+int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int64_t nb, const float* xq_batch, int k,
+                        int cap, int* d_overflow, cudaStream_t s) {
+    const int64_t N = ix->ntotal;
+    const int64_t nb_pad = round_up(nb, 256);
+    const int64_t first_panel = N < cap / 2 ? N : cap / 2;
+    FilterState st = filter_state(W, off, cap);
+    float* xq_f32 = W.xq_f32.as<float>() + off * ix->dp;
+    __nv_bfloat16* xq_bf16 = W.xq_bf16.as<__nv_bfloat16>() + off * ix->dp;
+    KNN_CHECK(launch_prep_queries(xq_batch, nb, nb_pad, ix->d, ix->dp, xq_f32, xq_bf16, W.xnorm2.as<float>() + off,
+                                  W.eps.as<float>() + off, ix->stats, ix->metric, s));
+    KNN_CHECK(launch_init_filter(st, nb, nb_pad, int(first_panel), s));
+    int64_t j0 = 0;
+    int panel = 0;
+    while (j0 < N) {
+        // rows seen: P, 4P, 8P, 16P, ... (P = first, densely stored panel): the second panel is taken 3P long
+        // because launches over a few thousand rows are too short to fill the machine
+        const int64_t len = panel == 0 ? first_panel : (panel == 1 ? 3 * j0 : j0);
+        const int64_t j1 = j0 + len < N ? j0 + len : N;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ix->profile) {
+            e0 = next_event(ix);
+            e1 = next_event(ix);
+            cudaEventRecord(e0, s);
         }
-        // thr now holds tau = (k-th best approx score) - 2 eps: rescoring everything at or above it
-        // covers the exact top-k.
-        KNN_CHECK(launch_rerank(W.xq_f32.as<float>(), W.xnorm2.as<float>(), nb, ix->dp, ix->xb_f32, ix->xb_bf16,
-                                ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, st_));
-        KNN_CHECK(launch_select_final(st.cand_scores, st.cand_ids, st.counts, cap, 0, nb, k, largest, D + q0 * k,
-                                      I + q0 * k, id_base, st_));
+        KNN_CHECK(gemm_filter_launch(ix->plan, xq_bf16, nb, nb_pad, ix->dp, ix->xb_bf16, N, ix->ynorm2, j0, j1, ix->metric,
+                                     panel == 0, st, s));
+        if (ix->profile) cudaEventRecord(e1, s);
+        ix->st_gemm_launches++;
+        KNN_CHECK(launch_tighten(st, W.eps.as<float>() + off, nb, k, 1, nullptr, d_overflow, s));
+        j0 = j1;
+        ++panel;
     }
-    if (nstreams == 2) {
-        for (int w = 0; w < 2; ++w) {
-            KNN_CHECK_CUDA(cudaEventRecord(ix->ev_join[w], ix->aux[w]));
-            KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_join[w], 0));
-        }
-    }
+    return KNN_OK;
+}
+
+// Finish phase of one batch: exact fp32 rescoring of every candidate at or above thr, then the sorted top-k.
+// `lower` (optional) is a lower bound of the TRUE k-th best score per query obtained elsewhere (other shards):
+// a row can only be in the global top-k if its approximate score is >= lower - eps.
+int tensor_finish_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int64_t nb, int k, int cap, const float* lower,
+                        float* D, int64_t* I, int64_t id_base, cudaStream_t s) {
+    const int largest = ix->metric == KNN_METRIC_INNER_PRODUCT;
+    FilterState st = filter_state(W, off, cap);
+    if (lower) KNN_CHECK(launch_apply_lower(st.thr, W.eps.as<float>() + off, lower, nb, s));
+    KNN_CHECK(launch_rerank(W.xq_f32.as<float>() + off * ix->dp, W.xnorm2.as<float>() + off, nb, ix->dp, ix->xb_f32,
+                            ix->xb_bf16, ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
+    KNN_CHECK(launch_select_final(st.cand_scores, st.cand_ids, st.counts, cap, 0, nb, k, largest, D, I, id_base, s));
+    return KNN_OK;
+}
+
+int redo_overflowed(knn_index* ix, int64_t nq, int64_t qb, int64_t nbatches, const float* xq_dev, int k, float* D,
+                    int64_t* I, int64_t id_base, cudaStream_t s) {
     // a candidate list that ran past its capacity (heavily duplicated / clustered scores) is never
     // truncated silently: that batch is redone with the exact scan.
     std::vector<int> h_overflow(size_t(nbatches), 0);
-    KNN_CHECK_CUDA(cudaMemcpyAsync(h_overflow.data(), d_overflow, sizeof(int) * size_t(nbatches), cudaMemcpyDeviceToHost, s));
+    KNN_CHECK_CUDA(cudaMemcpyAsync(h_overflow.data(), ix->overflow.p, sizeof(int) * size_t(nbatches), cudaMemcpyDeviceToHost, s));
     KNN_CHECK_CUDA(cudaStreamSynchronize(s));
     for (int64_t b = 0; b < nbatches; ++b) {
         if (!h_overflow[size_t(b)]) continue;
@@ -320,6 +317,32 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
         KNN_CHECK(search_exact(ix, nb, xq_dev + q0 * ix->d, k, D + q0 * k, I + q0 * k, id_base, s));
     }
     return KNN_OK;
+}
+
+int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
+                  cudaStream_t s) {
+    const int cap = candidate_capacity(k);
+    int64_t qb = ix->query_batch;
+    if (qb > nq) qb = nq;
+    qb = round_up(qb, 256);
+    const int64_t nbatches = (nq + qb - 1) / qb;
+    KNN_CHECK(tensor_ws_ensure(ix->ws1, qb, ix->dp, cap));
+    KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(nbatches)));
+    KNN_CHECK(tensor_prepare(ix));
+    KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(nbatches), s));
+    for (int64_t b = 0; b < nbatches; ++b) {
+        const int64_t q0 = b * qb;
+        const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
+        KNN_CHECK(tensor_filter_batch(ix, ix->ws1, 0, nb, xq_dev + q0 * ix->d, k, cap, ix->overflow.as<int>() + b, s));
+        KNN_CHECK(tensor_finish_batch(ix, ix->ws1, 0, nb, k, cap, nullptr, D + q0 * k, I + q0 * k, id_base, s));
+    }
+    return redo_overflowed(ix, nq, qb, nbatches, xq_dev, k, D, I, id_base, s);
+}
+
+bool use_tensor_path(const knn_index* ix, int64_t nq, int k) {
+    bool tensor = ix->path_param == 2 || (ix->path_param == 0 && nq >= ix->tensor_min_nq && ix->ntotal >= ix->tensor_min_n);
+    if (ix->ntotal < k) tensor = false;
+    return tensor;
 }
 
 int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* D, int64_t* I, int64_t id_base,
@@ -349,9 +372,7 @@ int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64,
                                  ix->metric == KNN_METRIC_INNER_PRODUCT, D, I, id_base, s);
         ix->last_path = 1;
     } else {
-        bool tensor = ix->path_param == 2 ||
-                      (ix->path_param == 0 && nq >= ix->tensor_min_nq && ix->ntotal >= ix->tensor_min_n);
-        if (tensor && ix->ntotal < k) tensor = false;
+        const bool tensor = use_tensor_path(ix, nq, k);
         ix->last_path = tensor ? 2 : 1;
         rc = tensor ? search_tensor(ix, nq, xq_dev, k, D, I, id_base, s) : search_exact(ix, nq, xq_dev, k, D, I, id_base, s);
     }
@@ -468,16 +489,8 @@ int knn_index_free(knn_index* ix) {
     for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xnorm2, &ix->eps, &ix->scores, &ix->lists_s, &ix->lists_i,
                       &ix->overflow, &ix->h_xq, &ix->h_D, &ix->h_I})
         b->release();
-    for (auto& W : ix->bws)
-        for (DevBuf* b : {&W.xq_f32, &W.xq_bf16, &W.xnorm2, &W.eps, &W.thr, &W.counts, &W.cand_s, &W.cand_i}) b->release();
-    for (int w = 0; w < 2; ++w) {
-        if (ix->aux[w]) {
-            cudaStreamSynchronize(ix->aux[w]);
-            cudaStreamDestroy(ix->aux[w]);
-        }
-        if (ix->ev_join[w]) cudaEventDestroy(ix->ev_join[w]);
-    }
-    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    for (knn_index::TensorWs* W : {&ix->ws1, &ix->ws2})
+        for (DevBuf* b : {&W->xq_f32, &W->xq_bf16, &W->xnorm2, &W->eps, &W->thr, &W->counts, &W->cand_s, &W->cand_i}) b->release();
     if (ix->xb_f32) cudaFree(ix->xb_f32);
     if (ix->xb_bf16) cudaFree(ix->xb_bf16);
     if (ix->ynorm2) cudaFree(ix->ynorm2);
@@ -594,6 +607,91 @@ int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, floa
     return KNN_OK;
 }
 
+int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* lower_dev, void* stream) {
+    if (!ix || nq <= 0 || k64 <= 0 || !xq_dev || !lower_dev) {
+        set_error("search_filter: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    if (k64 > KNN_MAX_K) {
+        set_error("search_filter: k=%lld exceeds KNN_MAX_K=%d", (long long)k64, KNN_MAX_K);
+        return KNN_ERR_LIMIT;
+    }
+    if (nq > (int64_t(1) << 17)) {
+        set_error("search_filter: at most 131072 queries per two-phase search (candidate lists stay resident)");
+        return KNN_ERR_LIMIT;
+    }
+    DeviceGuard g(ix->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int k = int(k64);
+    KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->add_event, 0));
+    ix->st_gemm_launches = 0;
+    ix->st_gemm_ms = 0;
+    ix->st_overflow_batches = 0;
+    ix->ev_used = 0;
+    auto& P = ix->pend;
+    P = knn_index::Pending();
+    P.nq = nq;
+    P.k = k;
+    P.tensor = ix->ntotal > 0 && use_tensor_path(ix, nq, k);
+    ix->last_path = P.tensor ? 2 : 1;
+    if (!P.tensor) {  // exact path: nothing to filter, no bound to offer
+        KNN_CHECK(launch_fill_f32(lower_dev, nq, -FLT_MAX, s));
+        P.active = true;
+        return KNN_OK;
+    }
+    P.cap = candidate_capacity(k);
+    P.qb = round_up(std::min<int64_t>(ix->query_batch, nq), 256);
+    P.nbatches = (nq + P.qb - 1) / P.qb;
+    KNN_CHECK(tensor_ws_ensure(ix->ws2, P.nbatches * P.qb, ix->dp, P.cap));
+    KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(P.nbatches)));
+    KNN_CHECK(tensor_prepare(ix));
+    KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(P.nbatches), s));
+    for (int64_t b = 0; b < P.nbatches; ++b) {
+        const int64_t q0 = b * P.qb;
+        const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
+        KNN_CHECK(tensor_filter_batch(ix, ix->ws2, q0, nb, xq_dev + q0 * ix->d, k, P.cap, ix->overflow.as<int>() + b, s));
+    }
+    // lower[q] = thr + eps = (k-th best approximate score) - eps: a lower bound of the true k-th best score
+    KNN_CHECK(launch_export_lower(ix->ws2.thr.as<float>(), ix->ws2.eps.as<float>(), nq, lower_dev, s));
+    P.active = true;
+    return KNN_OK;
+}
+
+int knn_index_search_finish_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, const float* lower_dev,
+                                float* D_dev, int64_t* I_dev, int64_t id_base, void* stream) {
+    if (!ix || !xq_dev || !D_dev || !I_dev) {
+        set_error("search_finish: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    auto& P = ix->pend;
+    if (!P.active || P.nq != nq || P.k != int(k64)) {
+        set_error("search_finish: no matching search_filter call is pending");
+        return KNN_ERR_INVALID;
+    }
+    DeviceGuard g(ix->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    P.active = false;
+    if (!P.tensor) return search_dev_impl(ix, nq, xq_dev, k64, D_dev, I_dev, id_base, s);
+    const long long launches0 = g_launches.load();
+    for (int64_t b = 0; b < P.nbatches; ++b) {
+        const int64_t q0 = b * P.qb;
+        const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
+        KNN_CHECK(tensor_finish_batch(ix, ix->ws2, q0, nb, P.k, P.cap, lower_dev ? lower_dev + q0 : nullptr, D_dev + q0 * P.k,
+                                      I_dev + q0 * P.k, id_base, s));
+    }
+    KNN_CHECK(redo_overflowed(ix, nq, P.qb, P.nbatches, xq_dev, P.k, D_dev, I_dev, id_base, s));
+    if (ix->profile && ix->ev_used) {
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ix->ev_pool[i], ix->ev_pool[i + 1]);
+            ix->st_gemm_ms += ms;
+        }
+    }
+    ix->st_launches = g_launches.load() - launches0;
+    return KNN_OK;
+}
+
 int knn_index_reconstruct(knn_index* ix, int64_t i0, int64_t n, float* out) {
     if (!ix || i0 < 0 || n < 0 || i0 + n > ix->ntotal || (n > 0 && !out)) {
         set_error("reconstruct: invalid range");
@@ -640,7 +738,6 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
     else if (n == "l2_hints") ix->l2_hints = value != 0;
     else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);
-    else if (n == "streams" && (value == 1 || value == 2)) ix->streams = int(value);
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
     else {

@@ -428,6 +428,30 @@ tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __
     }
 }
 
+__global__ void export_lower_kernel(const float* __restrict__ thr, const float* __restrict__ eps, int64_t nq,
+                                    float* __restrict__ lower) {
+    const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float t = thr[q], e = eps[q];
+    lower[q] = (t <= -FLT_MAX || !(e < FLT_MAX)) ? -FLT_MAX : t + e;
+}
+
+__global__ void apply_lower_kernel(float* __restrict__ thr, const float* __restrict__ eps, const float* __restrict__ lower,
+                                   int64_t nq) {
+    const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float l = lower[q], e = eps[q];
+    if (l > -FLT_MAX && e < FLT_MAX) {
+        const float t = l - e;
+        if (t > thr[q]) thr[q] = t;
+    }
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 __global__ void init_filter_kernel(float* thr, int* counts, int64_t nq, int64_t nq_pad, int first_count) {
     const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q >= nq_pad) return;
@@ -483,6 +507,24 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
         tighten_kernel<<<unsigned(nq), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap, eps, k,
                                                     compact, overflow);
     }
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* lower, cudaStream_t s) {
+    export_lower_kernel<<<unsigned((nq + 255) / 256), 256, 0, s>>>(thr, eps, nq, lower);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_apply_lower(float* thr, const float* eps, const float* lower, int64_t nq, cudaStream_t s) {
+    apply_lower_kernel<<<unsigned((nq + 255) / 256), 256, 0, s>>>(thr, eps, lower, nq);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s) {
+    fill_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(p, n, v);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }

@@ -21,7 +21,10 @@ def shard_bounds(n: int, world: int):
 
 
 class ShardedIndexFlat:
-    def __init__(self, d: int, metric: int, group=None, device=None, index_factory=None, merge_fn=None, **index_kw):
+    TWO_PHASE_MAX_QUERIES = 131072  # limit of knn_index_search_filter_dev (candidate lists stay resident)
+
+    def __init__(self, d: int, metric: int, group=None, device=None, index_factory=None, merge_fn=None,
+                 exchange_bounds: bool = True, **index_kw):
         import torch.distributed as dist
 
         self._dist = dist
@@ -39,6 +42,7 @@ class ShardedIndexFlat:
             from .index import merge_topk
 
             merge_fn = merge_topk
+        self.exchange_bounds = exchange_bounds
         self.local = index_factory()
         self._merge = merge_fn
         # one (global_start, local_start, count) triple per add() call
@@ -97,13 +101,23 @@ class ShardedIndexFlat:
         import torch
 
         as_numpy = isinstance(x, np.ndarray)
-        D, I = self.local.search(x, k)
-        if as_numpy:
-            D, I = torch.from_numpy(D), torch.from_numpy(I)
-            backend = self._dist.get_backend(self.group) if self._dist.is_initialized() else "gloo"
-            if backend == "nccl":
-                dev = torch.device("cuda", self.local.device)
-                D, I = D.to(dev), I.to(dev)
+        two_phase = (self.world > 1 and self.exchange_bounds and hasattr(self.local, "search_filter")
+                     and x.shape[0] <= self.TWO_PHASE_MAX_QUERIES)
+        if two_phase:
+            # filter on every shard -> all-reduce(MAX) of the per-query lower bounds of the k-th best score ->
+            # each shard rescoring only what can still be in the global top-k
+            xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if as_numpy else x
+            lower = self.local.search_filter(xd, k)
+            self._dist.all_reduce(lower, op=self._dist.ReduceOp.MAX, group=self.group)
+            D, I = self.local.search_finish(lower, k)
+        else:
+            D, I = self.local.search(x, k)
+            if as_numpy:
+                D, I = torch.from_numpy(D), torch.from_numpy(I)
+                backend = self._dist.get_backend(self.group) if self._dist.is_initialized() else "gloo"
+                if backend == "nccl":
+                    dev = torch.device("cuda", self.local.device)
+                    D, I = D.to(dev), I.to(dev)
         I = self._to_global(I)
         if self.world > 1:
             nq, kk = D.shape

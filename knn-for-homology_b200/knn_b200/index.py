@@ -162,6 +162,32 @@ class IndexFlat:
             I[I >= 0] += int(id_base)
         return D, I
 
+    # -- two-phase search (row-sharded databases; see distributed.ShardedIndexFlat) ----------
+    def search_filter(self, x, k: int):
+        """Phase 1 on CUDA tensor x: returns `lower` (nq,) float32 - per query a lower bound of the true
+        k-th best score inside this shard.  Combine across shards with an element-wise max."""
+        import torch
+
+        x = self._dev_matrix(x)
+        lower = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+        _lib.check(self._lib.knn_index_search_filter_dev(self._h, x.shape[0], x.data_ptr(), int(k), lower.data_ptr(),
+                                                         _torch_stream(self.device)))
+        self._pending_x = x  # phase 2 needs the same queries (kept alive here)
+        return lower
+
+    def search_finish(self, lower, k: int, id_base: int = 0):
+        """Phase 2: exact rescoring of the candidates that survive the combined bound -> this shard's (D, I)."""
+        import torch
+
+        x = self._pending_x
+        self._pending_x = None
+        D = torch.empty((x.shape[0], int(k)), dtype=torch.float32, device=x.device)
+        I = torch.empty((x.shape[0], int(k)), dtype=torch.int64, device=x.device)
+        lower = lower.contiguous()
+        _lib.check(self._lib.knn_index_search_finish_dev(self._h, x.shape[0], x.data_ptr(), int(k), lower.data_ptr(),
+                                                         D.data_ptr(), I.data_ptr(), int(id_base), _torch_stream(self.device)))
+        return D, I
+
     def search_into(self, xq_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int) -> None:
         """Host-pointer search into caller-owned (e.g. pinned) buffers: the raw C-ABI call."""
         _lib.check(self._lib.knn_index_search(self._h, int(nq), int(xq_ptr), int(k), int(D_ptr), int(I_ptr)))

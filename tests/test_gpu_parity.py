@@ -395,3 +395,44 @@ def test_properties_at_scale(knn):
     xb_h = xb.cpu().numpy()
     D_ref, I_ref = fo.knn_flat(xb_h[sample], xb_h, 100, IP)
     check_parity(Dn[sample], In[sample], D_ref, I_ref, xb_h[sample], xb_h, IP, max_excused_frac=5e-3)
+
+
+@pytest.mark.parametrize("metric,normalize", [(IP, True), (L2, False)])
+def test_two_phase_sharded_search_equals_single_index(knn, metric, normalize):
+    """Row-sharded search with the cross-shard bound exchange (filter -> max of the per-query lower
+    bounds -> finish -> merge), emulated in one process with three ragged shards whose rows have
+    different norms (so their error bounds differ).  Must equal the unsharded search bit for bit."""
+    import torch
+
+    xq, xb = _data(300, 40000, 256, seed=21, normalize=normalize, scale=1.3)
+    if not normalize:
+        xb[25000:] *= 1.7  # the third shard gets a larger max norm -> larger eps
+    dev = torch.device("cuda:0")
+    tq, tb = torch.from_numpy(xq).to(dev), torch.from_numpy(xb).to(dev)
+    k = 64
+    full = knn.IndexFlat(256, metric)
+    full.set_param("path", 2)
+    full.add(tb)
+    D, I = full.search(tq, k)
+    bounds = [0, 9000, 25000, 40000]
+    shards = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        sh = knn.IndexFlat(256, metric)
+        sh.set_param("path", 2)
+        sh.add(tb[a:b])
+        shards.append(sh)
+    lowers = [sh.search_filter(tq, k) for sh in shards]
+    lower = torch.stack(lowers).max(dim=0).values
+    assert (lower >= lowers[0]).all() and (lower > lowers[0]).any()  # the exchange does raise bounds
+    Ds, Is = zip(*[sh.search_finish(lower, k, id_base=a) for sh, a in zip(shards, bounds[:-1])])
+    Dm, Im = knn.merge_topk(torch.stack(Ds), torch.stack(Is), metric)
+    assert torch.equal(Im, I) and torch.equal(Dm, D)
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    check_parity(Dm.cpu().numpy(), Im.cpu().numpy(), D_ref, I_ref, xq, xb, metric, max_excused_frac=1e-2)
+    # a shard on the exact path takes part too (its bound is -FLT_MAX)
+    small = knn.IndexFlat(256, metric)
+    small.add(tb[:100])
+    lo = small.search_filter(tq, k)
+    assert (lo == -np.finfo(np.float32).max).all()
+    d_, i_ = small.search_finish(lower, k)
+    assert i_.shape == (300, k)
