@@ -232,6 +232,21 @@ scan_f32_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, 
 
 // ---------------------------------------------------------------------------------------
 template <bool BF16DB>
+__device__ __forceinline__ float4 load_row4(const void* __restrict__ xb, uint32_t id, int dp, int c) {
+    if (BF16DB) {
+        uint2 p = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xb) + int64_t(id) * dp)[c];
+        float2 lo = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.x));
+        float2 hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xb) + int64_t(id) * dp) + c);
+}
+
+// One CTA per query, the query row in shared memory.  Each warp takes 32 list entries at a time with one
+// coalesced load, then walks the entries that passed the final threshold two at a time: the 16 independent
+// 16-byte loads per lane of two database rows are in flight before the FMAs consume them.  The FMA order per
+// (row, query) pair is the scan kernel's, so a pair gets the same bits whichever path scored it.
+template <bool BF16DB>
 __global__ void __launch_bounds__(kBlock)
 rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, int dp, const void* __restrict__ xb,
               const float* __restrict__ ynorm2, int metric, float* __restrict__ cand_scores,
@@ -250,49 +265,65 @@ rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, in
     const float t = tau[q];
     float* cs = cand_scores + q * int64_t(cap);
     uint32_t* ci = cand_ids + q * int64_t(cap);
-    for (int i = warp; i < cnt; i += kWarpsPerBlock) {
-        const float approx = cs[i];
-        const uint32_t id = ci[i];
-        if (!(approx >= t) || id == kInvalidId) {  // warp-uniform
-            if (lane == 0) ci[i] = kInvalidId;
-            continue;
+    const float xn = metric == KNN_METRIC_L2 ? xnorm2[q] : 0.f;
+    for (int base = warp * 32; base < cnt; base += kWarpsPerBlock * 32) {
+        const int i = base + lane;
+        float approx = 0.f;
+        uint32_t id = kInvalidId;
+        if (i < cnt) {
+            approx = cs[i];
+            id = ci[i];
         }
-        // 8 independent 16-byte loads per lane are issued before the FMAs that consume them (a 1024-d row
-        // is exactly one such round); the FMA order is the scan kernel's, so the bits are too.
-        float a = 0.f;
-        for (int c0 = lane; c0 < dp4; c0 += 8 * 32) {
-            float4 y[8];
+        const bool valid = (i < cnt) && (approx >= t) && id != kInvalidId;
+        unsigned mask = __ballot_sync(0xffffffffu, valid);
+        float res = 0.f;
+        while (mask) {  // warp-uniform
+            const int j0 = __ffs(int(mask)) - 1;
+            mask &= mask - 1;
+            const bool two = mask != 0;
+            const int j1 = two ? __ffs(int(mask)) - 1 : j0;
+            mask &= mask - 1;  // no-op when mask is already 0
+            const uint32_t id0 = __shfl_sync(0xffffffffu, id, j0);
+            const uint32_t id1 = __shfl_sync(0xffffffffu, id, j1);
+            float a0 = 0.f, a1 = 0.f;
+            for (int c0 = lane; c0 < dp4; c0 += 8 * 32) {
+                float4 y0[8], y1[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = c0 + u * 32;
-                if (c < dp4) {
-                    if (BF16DB) {
-                        uint2 p = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xb) + int64_t(id) * dp)[c];
-                        float2 lo = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.x));
-                        float2 hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.y));
-                        y[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                    } else {
-                        y[u] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xb) + int64_t(id) * dp) + c);
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + u * 32;
+                    if (c < dp4) {
+                        y0[u] = load_row4<BF16DB>(xb, id0, dp, c);
+                        if (two) y1[u] = load_row4<BF16DB>(xb, id1, dp, c);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + u * 32;
+                    if (c < dp4) {
+                        const float4 qv = sq[c];
+                        a0 = fmaf(y0[u].x, qv.x, a0); a0 = fmaf(y0[u].y, qv.y, a0);
+                        a0 = fmaf(y0[u].z, qv.z, a0); a0 = fmaf(y0[u].w, qv.w, a0);
+                        if (two) {
+                            a1 = fmaf(y1[u].x, qv.x, a1); a1 = fmaf(y1[u].y, qv.y, a1);
+                            a1 = fmaf(y1[u].z, qv.z, a1); a1 = fmaf(y1[u].w, qv.w, a1);
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = c0 + u * 32;
-                if (c < dp4) {
-                    const float4 qv = sq[c];
-                    a = fmaf(y[u].x, qv.x, a); a = fmaf(y[u].y, qv.y, a); a = fmaf(y[u].z, qv.z, a); a = fmaf(y[u].w, qv.w, a);
-                }
-            }
-        }
-        a = warp_sum(a);
-        if (lane == 0) {
-            float v = a;
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
             if (metric == KNN_METRIC_L2) {
-                v = xnorm2[q] + ynorm2[id] - 2.0f * v;
-                v = v < 0.f ? 0.f : v;
+                a0 = xn + ynorm2[id0] - 2.0f * a0;
+                a0 = a0 < 0.f ? 0.f : a0;
+                a1 = xn + ynorm2[id1] - 2.0f * a1;
+                a1 = a1 < 0.f ? 0.f : a1;
             }
-            cs[i] = v;
+            if (lane == j0) res = a0;
+            if (two && lane == j1) res = a1;
+        }
+        if (i < cnt) {
+            if (valid) cs[i] = res;
+            else ci[i] = kInvalidId;
         }
     }
 }

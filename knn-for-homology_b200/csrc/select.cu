@@ -336,29 +336,52 @@ tighten_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __restr
 }
 
 
-// Warp-per-query variant for small k (candidate lists of a few hundred entries): the keys live in
-// registers and the k-th largest is found by a bit-by-bit search (32 rounds of compare + warp
-// reduce) - no block-wide barriers, 8 queries per CTA.
+// Warp-per-query variant for small k (candidate lists of a few hundred entries).  The whole list is
+// loaded into registers with independent loads (one memory round trip), the k-th largest key is found by a
+// bit-by-bit search (32 rounds of compare + warp reduce), and the survivors are written back compacted - no
+// block-wide barriers, no dependent global loads, 8 queries per CTA.
 template <int MAXE>
-__device__ __forceinline__ uint32_t warp_kth_largest_reg(const float* __restrict__ cs, int cnt, int k, int lane) {
+__device__ __forceinline__ void warp_tighten_reg(float* __restrict__ cs, uint32_t* __restrict__ ci, int cnt, int k,
+                                                 float two_eps, float old_thr, int lane, float& thr_out, int& cnt_out) {
     uint32_t keys[MAXE];
+    uint32_t ids[MAXE];
 #pragma unroll
     for (int e = 0; e < MAXE; ++e) {
         const int i = e * 32 + lane;
-        const float s = i < cnt ? cs[i] : 0.f;
-        keys[e] = (i < cnt && s == s) ? orderable_f32(s) : 0u;
+        const float sc = i < cnt ? cs[i] : 0.f;
+        ids[e] = i < cnt ? ci[i] : kInvalidId;
+        keys[e] = (i < cnt && sc == sc) ? orderable_f32(sc) : 0u;
     }
-    uint32_t t = 0;
+    uint32_t kth = 0;
 #pragma unroll 1
     for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t cand = t | (1u << bit);
+        const uint32_t cand = kth | (1u << bit);
         int c = 0;
 #pragma unroll
         for (int e = 0; e < MAXE; ++e) c += keys[e] >= cand ? 1 : 0;
         c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= k) t = cand;  // at least k keys are >= cand: the k-th largest has this bit pattern so far
+        if (c >= k) kth = cand;  // at least k keys are >= cand: the k-th largest starts with these bits
     }
-    return t;
+    float t = from_orderable_f32(kth) - two_eps;
+    if (!(t == t)) t = -FLT_MAX;
+    if (old_thr > t) t = old_thr;
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        if (e * 32 < cnt) {  // warp-uniform
+            const float sc = from_orderable_f32(keys[e]);
+            const bool keep = (sc >= t) && ids[e] != kInvalidId;
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int p = base + __popc(ballot & ((1u << lane) - 1u));
+                cs[p] = sc;
+                ci[p] = ids[e];
+            }
+            base += __popc(ballot);
+        }
+    }
+    thr_out = t;
+    cnt_out = base;
 }
 
 __device__ __forceinline__ uint32_t warp_kth_largest_mem(const float* __restrict__ cs, int cnt, int k, int lane) {
@@ -385,6 +408,8 @@ tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __
     const int64_t q = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (q >= nq) return;
     int cnt = counts[q];
+    const float two_eps = 2.0f * eps[q];
+    const float old = thr[q];
     if (cnt > cap) {
         if (lane == 0) atomicExch(overflow, 1);
         cnt = cap;
@@ -392,35 +417,41 @@ tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __
     if (cnt < k || cnt == 0) return;  // fewer than k candidates seen: everything stays a candidate
     float* cs = cand_scores + q * int64_t(cap);
     uint32_t* ci = cand_ids + q * int64_t(cap);
-    uint32_t kth;
-    if (cnt <= 16 * 32) kth = warp_kth_largest_reg<16>(cs, cnt, k, lane);
-    else if (cnt <= 32 * 32) kth = warp_kth_largest_reg<32>(cs, cnt, k, lane);
-    else kth = warp_kth_largest_mem(cs, cnt, k, lane);
-    float t = from_orderable_f32(kth) - 2.0f * eps[q];
-    if (!(t == t)) t = -FLT_MAX;
-    const float old = thr[q];
-    if (old > t) t = old;
-    // ordered in-place compaction, 32 entries at a time (a chunk is read completely before it is written,
-    // and writes land at or before positions that were already read)
-    int base = 0;
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
-        const int i = c0 + lane;
-        float s = 0.f;
-        uint32_t id = kInvalidId;
-        bool keep = false;
-        if (i < cnt) {
-            s = cs[i];
-            id = ci[i];
-            keep = (s >= t) && id != kInvalidId;
+    float t;
+    int base;
+    if (cnt <= 8 * 32) {
+        warp_tighten_reg<8>(cs, ci, cnt, k, two_eps, old, lane, t, base);
+    } else if (cnt <= 16 * 32) {
+        warp_tighten_reg<16>(cs, ci, cnt, k, two_eps, old, lane, t, base);
+    } else if (cnt <= 32 * 32) {
+        warp_tighten_reg<32>(cs, ci, cnt, k, two_eps, old, lane, t, base);
+    } else {
+        const uint32_t kth = warp_kth_largest_mem(cs, cnt, k, lane);
+        t = from_orderable_f32(kth) - two_eps;
+        if (!(t == t)) t = -FLT_MAX;
+        if (old > t) t = old;
+        // ordered in-place compaction, 32 entries at a time (a chunk is read completely before it is written,
+        // and writes land at or before positions that were already read)
+        base = 0;
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const int i = c0 + lane;
+            float s = 0.f;
+            uint32_t id = kInvalidId;
+            bool keep = false;
+            if (i < cnt) {
+                s = cs[i];
+                id = ci[i];
+                keep = (s >= t) && id != kInvalidId;
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int p = base + __popc(ballot & ((1u << lane) - 1u));
+                cs[p] = s;
+                ci[p] = id;
+            }
+            base += __popc(ballot);
+            __syncwarp();
         }
-        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int p = base + __popc(ballot & ((1u << lane) - 1u));
-            cs[p] = s;
-            ci[p] = id;
-        }
-        base += __popc(ballot);
-        __syncwarp();
     }
     if (lane == 0) {
         thr[q] = t;
