@@ -257,7 +257,11 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
                         int cap, int* d_overflow, cudaStream_t s) {
     const int64_t N = ix->ntotal;
     const int64_t nb_pad = round_up(nb, 256);
-    const int64_t first_panel = N < cap / 2 ? N : cap / 2;
+    // first panel: stored densely (every score), sized so that the list it leaves fits the register-resident
+    // tighten (<= 1024 entries) for small k, and holds well over k rows for large k
+    int64_t first_panel = std::max<int64_t>(1024, round_up(4 * int64_t(k), 256));
+    if (first_panel > cap / 2) first_panel = cap / 2;
+    if (first_panel > N) first_panel = N;
     FilterState st = filter_state(W, off, cap);
     float* xq_f32 = W.xq_f32.as<float>() + off * ix->dp;
     __nv_bfloat16* xq_bf16 = W.xq_bf16.as<__nv_bfloat16>() + off * ix->dp;
