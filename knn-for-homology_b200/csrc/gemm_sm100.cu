@@ -47,8 +47,10 @@ struct Cfg {
     static constexpr uint32_t kBytesA = BM * BK * 2;
     static constexpr uint32_t kBytesB = kRowsB * BK * 2;
     static constexpr uint32_t kBytesStage = kBytesA + kBytesB;
-    static constexpr size_t kSmemBytes =
-        size_t(kStages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (512 * 8 + 8 * 32 * 16) + 16 /*EpilogueSmem*/;
+    static constexpr size_t smem_bytes(int stages) {
+        return size_t(stages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (512 * 8 + 8 * 32 * 16) + 16 /*EpilogueSmem*/;
+    }
+    static constexpr size_t kSmemBytes = smem_bytes(kStages);
     // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
     // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 (M = 256 for a CTA pair).
     static constexpr uint32_t kInstrDesc =
@@ -232,6 +234,7 @@ struct GemmArgs {
     uint32_t* cand_ids;
     int cap;
     uint64_t hint_q, hint_db;  // L2 eviction-priority policies of the two TMA streams
+    int stages;                // shared-memory pipeline depth
     int debug_skip_epilogue;   // experiments only: accumulators are not read (results are then meaningless)
 };
 
@@ -298,10 +301,11 @@ template <int CG, bool L2, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
     using C = Cfg<CG>;
+    const int nstages = args.stages;  // depth of the TMA -> MMA shared-memory ring (<= kMaxStages)
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms; plain pointer arithmetic keeps the shared address space
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + size_t(C::kStages) * C::kBytesStage);
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + size_t(nstages) * C::kBytesStage);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = args.m_tiles * args.n_tiles;
@@ -313,7 +317,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (warp == kProducerWarp && lane == 0) {
         prefetch_tmap(&map_q);
         prefetch_tmap(&map_db);
-        for (int i = 0; i < C::kStages; ++i) {
+        for (int i = 0; i < nstages; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->empty[i], 1);
         }
@@ -352,7 +356,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         tma_load_2d_pair(sa, &map_q, &bars->full[stage], kb * BK, row_q, args.hint_q);
                         tma_load_2d_pair(sb, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
                     }
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -380,7 +384,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         umma_bf16<CG>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), C::kInstrDesc, (kb | k) ? 1u : 0u);
                     }
                     umma_commit<CG>(&bars->empty[stage]);  // smem slot reusable once these MMAs have read it
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit<CG>(&bars->acc_full[acc]);  // accumulator complete -> epilogue (of both CTAs)
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -391,7 +395,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        EpilogueSmem* es = reinterpret_cast<EpilogueSmem*>(smem + size_t(C::kStages) * C::kBytesStage + 256);
+        EpilogueSmem* es = reinterpret_cast<EpilogueSmem*>(smem + size_t(nstages) * C::kBytesStage + 256);
         uint2* stash = es->stash[warp];
         float4* dump = es->dump[warp];
         int* stash_count = &es->count[warp];
@@ -543,11 +547,13 @@ struct GemmPlan {
     int cta_group = 2;  // 1: one CTA per tile, 2: CTA pairs (tcgen05 cta_group::2)
     int l2_hints = 0;   // 1: queries evict-last, database evict-first
     int debug_skip_epilogue = 0;
+    int stages = 0;     // 0: default depth of the variant (4 for cta_group 1, 6 for cta_group 2)
 };
 
 void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
 void gemm_plan_set_l2_hints(GemmPlan* p, int on) { p->l2_hints = on; }
 void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue) { p->debug_skip_epilogue = skip_epilogue; }
+void gemm_plan_set_stages(GemmPlan* p, int stages) { p->stages = stages; }
 int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
@@ -605,7 +611,7 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(units * CG), 1, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = Cfg<CG>::kSmemBytes;
+    cfg.dynamicSmemBytes = Cfg<CG>::smem_bytes(a.stages);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -649,6 +655,8 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
     a.cand_ids = st.cand_ids;
     a.cap = st.cap;
     a.debug_skip_epilogue = p->debug_skip_epilogue;
+    a.stages = cg == 1 ? Cfg<1>::kStages : Cfg<2>::kStages;
+    if (p->stages >= 2 && p->stages <= a.stages) a.stages = p->stages;
     a.hint_q = p->l2_hints ? kEvictLast : kEvictNormal;
     a.hint_db = p->l2_hints ? kEvictFirst : kEvictNormal;
     const bool l2 = metric == KNN_METRIC_L2;

@@ -111,6 +111,8 @@ struct knn_index {
     int cta_group = 2;
     int l2_hints = 0;
     int debug_skip_epilogue = 0;
+    int gemm_stages = 0;
+    int panel_ratio = 0;  // 0: automatic
     // statistics of the last search
     int last_path = 0;
     long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_rerank_pairs = 0;
@@ -247,6 +249,7 @@ int tensor_prepare(knn_index* ix) {
     gemm_plan_set_cta_group(ix->plan, ix->cta_group);
     gemm_plan_set_l2_hints(ix->plan, ix->l2_hints);
     gemm_plan_set_debug(ix->plan, ix->debug_skip_epilogue);
+    gemm_plan_set_stages(ix->plan, ix->gemm_stages);
     return KNN_OK;
 }
 
@@ -262,6 +265,7 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     int64_t first_panel = std::max<int64_t>(1024, round_up(4 * int64_t(k), 256));
     if (first_panel > cap / 2) first_panel = cap / 2;
     if (first_panel > N) first_panel = N;
+    const int ratio = ix->panel_ratio >= 2 ? ix->panel_ratio : (k <= 128 ? 8 : (k <= 512 ? 4 : 2));
     FilterState st = filter_state(W, off, cap);
     float* xq_f32 = W.xq_f32.as<float>() + off * ix->dp;
     __nv_bfloat16* xq_bf16 = W.xq_bf16.as<__nv_bfloat16>() + off * ix->dp;
@@ -271,9 +275,10 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     int64_t j0 = 0;
     int panel = 0;
     while (j0 < N) {
-        // rows seen: P, 4P, 8P, 16P, ... (P = first, densely stored panel): the second panel is taken 3P long
-        // because launches over a few thousand rows are too short to fill the machine
-        const int64_t len = panel == 0 ? first_panel : (panel == 1 ? 3 * j0 : j0);
+        // rows seen after each panel: P, rP, r^2 P, ... (P = first, densely stored panel).  The expected number
+        // of survivors appended between two tightenings is k' ln r whatever r is (k' = rows within 2 eps of the
+        // k-th), so a larger ratio costs the same appends in fewer launches - bounded by the list capacity.
+        const int64_t len = panel == 0 ? first_panel : (ratio - 1) * j0;
         const int64_t j1 = j0 + len < N ? j0 + len : N;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ix->profile) {
@@ -741,6 +746,8 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "profile") ix->profile = value != 0;
     else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
     else if (n == "l2_hints") ix->l2_hints = value != 0;
+    else if (n == "gemm_stages" && value >= 0 && value <= 6) ix->gemm_stages = int(value);
+    else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
     else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;

@@ -15,7 +15,7 @@ import torch
 import knn_b200
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
-nq, d, k = 32768, 1024, 100
+nq, d, k = (int(sys.argv[3]) if len(sys.argv) > 3 else 32768), 1024, 100
 dev = torch.device("cuda:0")
 variants = [dict(cta_group=2, debug_skip_epilogue=0, streams=1), dict(cta_group=2, debug_skip_epilogue=1, streams=1),
             dict(cta_group=1, debug_skip_epilogue=1, streams=1), dict(cta_group=2, debug_skip_epilogue=0, streams=2)]
@@ -59,7 +59,7 @@ for rep in range(3):
     for v in variants:
         for name, val in v.items():
             idx.set_param(name, val)
-        prof = v.get("streams", 1) == 1
+        prof = True
         idx.set_param("profile", 1 if prof else 0)
         idx.search(xq, k)
         torch.cuda.synchronize()
