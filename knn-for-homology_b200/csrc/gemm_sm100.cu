@@ -42,7 +42,9 @@ constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a 
 
 template <int CG>
 struct Cfg {
-    static constexpr int kStages = CG == 1 ? 4 : 6;
+    // measured on B200: for the CTA pair 4, 5 and 6 stages of 32 KB run the same; 4 leaves ~60 KB of shared
+    // memory per SM to the CUDA-core kernels of the other query batch
+    static constexpr int kStages = 4;
     static constexpr int kRowsB = BN / CG;  // database rows staged by one CTA
     static constexpr uint32_t kBytesA = BM * BK * 2;
     static constexpr uint32_t kBytesB = kRowsB * BK * 2;
@@ -547,7 +549,7 @@ struct GemmPlan {
     int cta_group = 2;  // 1: one CTA per tile, 2: CTA pairs (tcgen05 cta_group::2)
     int l2_hints = 0;   // 1: queries evict-last, database evict-first
     int debug_skip_epilogue = 0;
-    int stages = 0;     // 0: default depth of the variant (4 for cta_group 1, 6 for cta_group 2)
+    int stages = 0;     // 0: default depth (4)
 };
 
 void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
@@ -602,7 +604,8 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     auto kern = gemm_filter_kernel<CG, L2, DENSE>;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
-        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<CG>::kSmemBytes)));
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(Cfg<CG>::smem_bytes(CG == 1 ? 4 : kMaxStages))));
         attr_done = true;
     }
     const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;
@@ -656,7 +659,7 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
     a.cap = st.cap;
     a.debug_skip_epilogue = p->debug_skip_epilogue;
     a.stages = cg == 1 ? Cfg<1>::kStages : Cfg<2>::kStages;
-    if (p->stages >= 2 && p->stages <= a.stages) a.stages = p->stages;
+    if (p->stages >= 2 && p->stages <= (cg == 1 ? 4 : kMaxStages)) a.stages = p->stages;
     a.hint_q = p->l2_hints ? kEvictLast : kEvictNormal;
     a.hint_db = p->l2_hints ? kEvictFirst : kEvictNormal;
     const bool l2 = metric == KNN_METRIC_L2;

@@ -55,11 +55,12 @@ knn_b200.normalize_L2(xq)
 
 cublas_reference()
 STEPS = 6
+DEFAULTS = dict(cta_group=2, debug_skip_epilogue=0, streams=1, gemm_stages=0, panel_ratio=0, query_batch=16384)
 for rep in range(3):
     for v in variants:
-        for name, val in v.items():
+        for name, val in dict(DEFAULTS, **v).items():
             idx.set_param(name, val)
-        prof = True
+        prof = v.get("streams", 1) == 1
         idx.set_param("profile", 1 if prof else 0)
         idx.search(xq, k)
         torch.cuda.synchronize()
