@@ -606,6 +606,10 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     if (!attr_done) {
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(Cfg<CG>::smem_bytes(CG == 1 ? 4 : kMaxStages))));
+        // Ask for the largest shared-memory carveout (228 KB) although this CTA needs ~162 KB: the SM's carveout
+        // cannot change while a CTA is resident, and with the snug 164 KB configuration no other kernel that
+        // uses shared memory could join this persistent CTA on its SM (measured: tools/micro/overlap_test.cu).
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;
