@@ -45,22 +45,6 @@ constexpr int kSelectThreads = 512;
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-// Every kernel of the library asks for the largest shared-memory carveout: kernels of two query batches
-// co-run on an SM (tensor-core GEMM of one, CUDA-core kernels of the other) and the carveout of an SM cannot
-// change while a CTA is resident.
-template <class Kernel>
-inline void prefer_max_smem_once(Kernel kern, bool& done) {
-    if (!done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        done = true;
-    }
-}
-#define KNN_PREFER_MAX_SMEM(kern)                          \
-    do {                                                   \
-        static bool done__ = false;                        \
-        knn::prefer_max_smem_once(kern, done__);           \
-    } while (0)
-
 // ---- ordering keys --------------------------------------------------------------------
 // 64-bit composite key, larger = better:  [ orderable(score) | ~id ].  All valid keys are
 // distinct (ids are), so "top-k by key" has no ties and the rule "equal score -> lower id

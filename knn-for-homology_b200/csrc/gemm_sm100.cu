@@ -42,8 +42,7 @@ constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a 
 
 template <int CG>
 struct Cfg {
-    // measured on B200: for the CTA pair 4, 5 and 6 stages of 32 KB run the same; 4 leaves ~60 KB of shared
-    // memory per SM to the CUDA-core kernels of the other query batch
+    // measured on B200: for the CTA pair 4, 5 and 6 stages of 32 KB run the same
     static constexpr int kStages = 4;
     static constexpr int kRowsB = BN / CG;  // database rows staged by one CTA
     static constexpr uint32_t kBytesA = BM * BK * 2;
@@ -606,10 +605,6 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     if (!attr_done) {
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(Cfg<CG>::smem_bytes(CG == 1 ? 4 : kMaxStages))));
-        // Ask for the largest shared-memory carveout (228 KB) although this CTA needs ~162 KB: the SM's carveout
-        // cannot change while a CTA is resident, and with the snug 164 KB configuration no other kernel that
-        // uses shared memory could join this persistent CTA on its SM (measured: tools/micro/overlap_test.cu).
-        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;

@@ -96,13 +96,8 @@ struct knn_index {
     struct TensorWs {
         DevBuf xq_f32, xq_bf16, xnorm2, eps, thr, counts, cand_s, cand_i;
     };
-    TensorWs ws1[2];  // one query batch per stream (single-call search)
+    TensorWs ws1;  // one query batch (single-call search)
     TensorWs ws2;  // all queries of a two-phase search (filter ... exchange ... finish)
-    // two query batches in flight: the CUDA-core kernels of one batch (tighten, rerank, select) run under the
-    // tensor-core GEMM of the other (the GEMM CTA leaves ~60 KB of shared memory per SM free for them)
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    int streams = 2;
     struct Pending {
         bool active = false, tensor = false;
         int64_t nq = 0, qb = 0, nbatches = 0;
@@ -333,37 +328,6 @@ int redo_overflowed(knn_index* ix, int64_t nq, int64_t qb, int64_t nbatches, con
     return KNN_OK;
 }
 
-int ensure_aux(knn_index* ix) {
-    if (ix->aux[0]) return KNN_OK;
-    for (int i = 0; i < 2; ++i) {
-        KNN_CHECK_CUDA(cudaStreamCreateWithFlags(&ix->aux[i], cudaStreamNonBlocking));
-        KNN_CHECK_CUDA(cudaEventCreateWithFlags(&ix->ev_join[i], cudaEventDisableTiming));
-    }
-    KNN_CHECK_CUDA(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
-    return KNN_OK;
-}
-
-// Number of streams the batches of one call are spread over (event timing of the GEMM launches needs them
-// serialised, so profile mode uses one).
-int batch_streams(knn_index* ix, int64_t nbatches) { return (ix->streams >= 2 && nbatches >= 2 && !ix->profile) ? 2 : 1; }
-
-int fork_streams(knn_index* ix, int n, cudaStream_t s) {
-    if (n < 2) return KNN_OK;
-    KNN_CHECK(ensure_aux(ix));
-    KNN_CHECK_CUDA(cudaEventRecord(ix->ev_fork, s));
-    for (int w = 0; w < 2; ++w) KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->aux[w], ix->ev_fork, 0));
-    return KNN_OK;
-}
-
-int join_streams(knn_index* ix, int n, cudaStream_t s) {
-    if (n < 2) return KNN_OK;
-    for (int w = 0; w < 2; ++w) {
-        KNN_CHECK_CUDA(cudaEventRecord(ix->ev_join[w], ix->aux[w]));
-        KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_join[w], 0));
-    }
-    return KNN_OK;
-}
-
 int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
                   cudaStream_t s) {
     const int cap = candidate_capacity(k);
@@ -371,21 +335,16 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     if (qb > nq) qb = nq;
     qb = round_up(qb, 256);
     const int64_t nbatches = (nq + qb - 1) / qb;
-    const int ns = batch_streams(ix, nbatches);
-    for (int w = 0; w < ns; ++w) KNN_CHECK(tensor_ws_ensure(ix->ws1[w], qb, ix->dp, cap));
+    KNN_CHECK(tensor_ws_ensure(ix->ws1, qb, ix->dp, cap));
     KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(nbatches)));
     KNN_CHECK(tensor_prepare(ix));
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(nbatches), s));
-    KNN_CHECK(fork_streams(ix, ns, s));
     for (int64_t b = 0; b < nbatches; ++b) {
         const int64_t q0 = b * qb;
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
-        const int w = ns == 2 ? int(b & 1) : 0;
-        cudaStream_t sb = ns == 2 ? ix->aux[w] : s;
-        KNN_CHECK(tensor_filter_batch(ix, ix->ws1[w], 0, nb, xq_dev + q0 * ix->d, k, cap, ix->overflow.as<int>() + b, sb));
-        KNN_CHECK(tensor_finish_batch(ix, ix->ws1[w], 0, nb, k, cap, nullptr, D + q0 * k, I + q0 * k, id_base, sb));
+        KNN_CHECK(tensor_filter_batch(ix, ix->ws1, 0, nb, xq_dev + q0 * ix->d, k, cap, ix->overflow.as<int>() + b, s));
+        KNN_CHECK(tensor_finish_batch(ix, ix->ws1, 0, nb, k, cap, nullptr, D + q0 * k, I + q0 * k, id_base, s));
     }
-    KNN_CHECK(join_streams(ix, ns, s));
     return redo_overflowed(ix, nq, qb, nbatches, xq_dev, k, D, I, id_base, s);
 }
 
@@ -539,15 +498,7 @@ int knn_index_free(knn_index* ix) {
     for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xnorm2, &ix->eps, &ix->scores, &ix->lists_s, &ix->lists_i,
                       &ix->overflow, &ix->h_xq, &ix->h_D, &ix->h_I})
         b->release();
-    for (int w = 0; w < 2; ++w) {
-        if (ix->aux[w]) {
-            cudaStreamSynchronize(ix->aux[w]);
-            cudaStreamDestroy(ix->aux[w]);
-        }
-        if (ix->ev_join[w]) cudaEventDestroy(ix->ev_join[w]);
-    }
-    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
-    for (knn_index::TensorWs* W : {&ix->ws1[0], &ix->ws1[1], &ix->ws2})
+    for (knn_index::TensorWs* W : {&ix->ws1, &ix->ws2})
         for (DevBuf* b : {&W->xq_f32, &W->xq_bf16, &W->xnorm2, &W->eps, &W->thr, &W->counts, &W->cand_s, &W->cand_i}) b->release();
     if (ix->xb_f32) cudaFree(ix->xb_f32);
     if (ix->xb_bf16) cudaFree(ix->xb_bf16);
@@ -704,15 +655,11 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(P.nbatches)));
     KNN_CHECK(tensor_prepare(ix));
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(P.nbatches), s));
-    const int ns = batch_streams(ix, P.nbatches);
-    KNN_CHECK(fork_streams(ix, ns, s));
     for (int64_t b = 0; b < P.nbatches; ++b) {
         const int64_t q0 = b * P.qb;
         const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
-        KNN_CHECK(tensor_filter_batch(ix, ix->ws2, q0, nb, xq_dev + q0 * ix->d, k, P.cap, ix->overflow.as<int>() + b,
-                                      ns == 2 ? ix->aux[b & 1] : s));
+        KNN_CHECK(tensor_filter_batch(ix, ix->ws2, q0, nb, xq_dev + q0 * ix->d, k, P.cap, ix->overflow.as<int>() + b, s));
     }
-    KNN_CHECK(join_streams(ix, ns, s));
     // lower[q] = thr + eps = (k-th best approximate score) - eps: a lower bound of the true k-th best score
     KNN_CHECK(launch_export_lower(ix->ws2.thr.as<float>(), ix->ws2.eps.as<float>(), nq, lower_dev, s));
     P.active = true;
@@ -735,15 +682,12 @@ int knn_index_search_finish_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     P.active = false;
     if (!P.tensor) return search_dev_impl(ix, nq, xq_dev, k64, D_dev, I_dev, id_base, s);
     const long long launches0 = g_launches.load();
-    const int ns = batch_streams(ix, P.nbatches);
-    KNN_CHECK(fork_streams(ix, ns, s));
     for (int64_t b = 0; b < P.nbatches; ++b) {
         const int64_t q0 = b * P.qb;
         const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
         KNN_CHECK(tensor_finish_batch(ix, ix->ws2, q0, nb, P.k, P.cap, lower_dev ? lower_dev + q0 : nullptr, D_dev + q0 * P.k,
-                                      I_dev + q0 * P.k, id_base, ns == 2 ? ix->aux[b & 1] : s));
+                                      I_dev + q0 * P.k, id_base, s));
     }
-    KNN_CHECK(join_streams(ix, ns, s));
     KNN_CHECK(redo_overflowed(ix, nq, P.qb, P.nbatches, xq_dev, P.k, D_dev, I_dev, id_base, s));
     if (ix->profile && ix->ev_used) {
         KNN_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -802,7 +746,6 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "profile") ix->profile = value != 0;
     else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
     else if (n == "l2_hints") ix->l2_hints = value != 0;
-    else if (n == "streams" && (value == 1 || value == 2)) ix->streams = int(value);
     else if (n == "gemm_stages" && value >= 0 && value <= 6) ix->gemm_stages = int(value);
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
     else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);

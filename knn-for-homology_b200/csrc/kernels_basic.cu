@@ -355,8 +355,6 @@ int launch_prep_queries(const float* xq, int64_t nq, int64_t nq_pad, int d, int 
     if (nq <= 0) return KNN_OK;
     // eps doubles as scratch for |dx|^2 until query_eps_kernel overwrites it
     const int vec_ok = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(xq) % 16 == 0);
-    KNN_PREFER_MAX_SMEM(ingest_rows_kernel);
-    KNN_PREFER_MAX_SMEM(query_eps_kernel);
     ingest_rows_kernel<<<grid_for_rows(nq, kWarpsPerBlock, 8), kBlock, 0, s>>>(xq, nq, d, dp, xq_f32, xq_bf16,
                                                                                 xnorm2, eps, nullptr, vec_ok, 0);
     KNN_CHECK_LAUNCH();
@@ -425,13 +423,11 @@ int launch_rerank(const float* xq_f32, const float* xnorm2, int64_t nq, int dp, 
     if (xb_f32) {
         auto kern = rerank_kernel<false>;
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        KNN_PREFER_MAX_SMEM(kern);
         kern<<<unsigned(nq), kBlock, smem, s>>>(xq_f32, xnorm2, dp, xb_f32, ynorm2, metric, cand_scores, cand_ids,
                                                 counts, tau, cap);
     } else {
         auto kern = rerank_kernel<true>;
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        KNN_PREFER_MAX_SMEM(kern);
         kern<<<unsigned(nq), kBlock, smem, s>>>(xq_f32, xnorm2, dp, xb_bf16, ynorm2, metric, cand_scores, cand_ids,
                                                 counts, tau, cap);
     }

@@ -513,7 +513,6 @@ int launch_select_final(const float* list_scores, const uint32_t* list_ids, cons
                         int64_t fixed_len, int64_t nq, int k, int largest, float* D, int64_t* I, int64_t id_base,
                         cudaStream_t s) {
     if (nq <= 0) return KNN_OK;
-    KNN_PREFER_MAX_SMEM(select_final_kernel);
     select_final_kernel<<<unsigned(nq), kSelectThreads, 0, s>>>(list_scores, list_ids, counts, list_ld, fixed_len, k,
                                                                 largest, D, I, id_base);
     KNN_CHECK_LAUNCH();
@@ -532,8 +531,6 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
                    cudaStream_t s) {
     (void)tau_out;
     if (nq <= 0) return KNN_OK;
-    KNN_PREFER_MAX_SMEM(tighten_warp_kernel);
-    KNN_PREFER_MAX_SMEM(tighten_kernel);
     if (k <= 256 && compact) {
         tighten_warp_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap,
                                                                    eps, nq, k, overflow);
@@ -552,7 +549,6 @@ int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* l
 }
 
 int launch_apply_lower(float* thr, const float* eps, const float* lower, int64_t nq, cudaStream_t s) {
-    KNN_PREFER_MAX_SMEM(apply_lower_kernel);
     apply_lower_kernel<<<unsigned((nq + 255) / 256), 256, 0, s>>>(thr, eps, lower, nq);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
@@ -565,7 +561,6 @@ int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s) {
 }
 
 int launch_init_filter(FilterState st, int64_t nq, int64_t nq_pad, int first_count, cudaStream_t s) {
-    KNN_PREFER_MAX_SMEM(init_filter_kernel);
     init_filter_kernel<<<unsigned((nq_pad + 255) / 256), 256, 0, s>>>(st.thr, st.counts, nq, nq_pad, first_count);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
