@@ -62,6 +62,15 @@ def measured_peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the GEMM kernel from the committed `ncu --set full` capture (profiles/)."""
+    f = REPO / "profiles" / "gemm_traffic.json"
+    if not f.exists():
+        return None, "no ncu capture committed"
+    d = json.loads(f.read_text())
+    return d["dram_bytes_per_launch"], d["note"]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -271,11 +280,12 @@ def main():
         flops_per_step = 2.0 * args.nq * n_shard * D_DIM
         achieved = flops_per_step * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         peak = peaks["tflops_sustained"]
+        traffic, traffic_note = ncu_traffic()
         roofline = {"bound": "tensor", "kernel": "gemm_filter_kernel (tcgen05 bf16, fused threshold filter)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None, "peak_kind": "sustained, " + peaks["source"],
                     "frac_of_burst": (achieved / peaks["tflops_burst"]) if achieved else None,
-                    "traffic": None, "launches": gemm_launches, "kernel_ms_per_step": gemm_ms / args.steps,
+                    "traffic": traffic, "traffic_note": traffic_note, "launches": gemm_launches, "kernel_ms_per_step": gemm_ms / args.steps,
                     "algorithmic_flop_per_launch_avg": flops_per_step * args.steps / max(1, gemm_launches)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -288,7 +298,8 @@ def main():
             "metric": "queries/s at 1024-d, k=%d, exact flat inner-product search" % args.k,
             "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 tensor-core filter + f32 exact rerank", "data": "synthetic",
+            "dtype": "bf16", "dtype_note": "bf16 x bf16 -> f32 tensor-core filter, then exact f32 rescoring: results equal f32 IndexFlatIP",
+            "data": "synthetic",
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
             "search_path": search_path, "cta_group": args.cta_group,
