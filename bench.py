@@ -274,6 +274,12 @@ def main():
     index.local.set_param("path", 0)
     parity_ok = bool(torch.equal(I[chk], I1) and torch.equal(D[chk], D1))
 
+    phases = None
+    if world > 1:  # one extra, untimed step with CUDA events around the phases of the sharded search
+        index.profile_phases = True
+        step_device()
+        index.profile_phases = False
+        phases = index.last_phases_ms
     if rank == 0:
         peaks = measured_peaks()
         n_shard = hi - lo
@@ -302,7 +308,7 @@ def main():
             "data": "synthetic",
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
-            "search_path": search_path, "cta_group": args.cta_group,
+            "search_path": search_path, "cta_group": args.cta_group, "phases_ms_rank0": phases,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -43,6 +43,8 @@ class ShardedIndexFlat:
 
             merge_fn = merge_topk
         self.exchange_bounds = exchange_bounds
+        self.profile_phases = False
+        self.last_phases_ms = None
         self.local = index_factory()
         self._merge = merge_fn
         # one (global_start, local_start, count) triple per add() call
@@ -101,6 +103,15 @@ class ShardedIndexFlat:
         import torch
 
         as_numpy = isinstance(x, np.ndarray)
+        marks = []
+
+        def mark(name):
+            if self.profile_phases:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         two_phase = (self.world > 1 and self.exchange_bounds and hasattr(self.local, "search_filter")
                      and x.shape[0] <= self.TWO_PHASE_MAX_QUERIES)
         if two_phase:
@@ -108,8 +119,11 @@ class ShardedIndexFlat:
             # each shard rescoring only what can still be in the global top-k
             xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if as_numpy else x
             lower = self.local.search_filter(xd, k)
+            mark("filter")
             self._dist.all_reduce(lower, op=self._dist.ReduceOp.MAX, group=self.group)
+            mark("all_reduce_bounds")
             D, I = self.local.search_finish(lower, k)
+            mark("finish")
         else:
             D, I = self.local.search(x, k)
             if as_numpy:
@@ -119,13 +133,19 @@ class ShardedIndexFlat:
                     dev = torch.device("cuda", self.local.device)
                     D, I = D.to(dev), I.to(dev)
         I = self._to_global(I)
+        mark("to_global")
         if self.world > 1:
             nq, kk = D.shape
             Dg = torch.empty((self.world * nq, kk), dtype=D.dtype, device=D.device)
             Ig = torch.empty((self.world * nq, kk), dtype=I.dtype, device=I.device)
             self._dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
             self._dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+            mark("all_gather")
             D, I = self._merge(Dg.view(self.world, nq, kk), Ig.view(self.world, nq, kk), self.metric_type)
+            mark("merge")
+        if marks:
+            torch.cuda.synchronize()
+            self.last_phases_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
         if as_numpy:
             return D.cpu().numpy(), I.cpu().numpy()
         return D, I
