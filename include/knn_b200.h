@@ -88,12 +88,15 @@ int knn_index_search_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_
 
 /* Two-phase search for a row-sharded database (new).  Phase 1 runs the
  * tensor-core filter over this shard and writes lower_dev[q], a lower bound of the TRUE k-th best score
- * of query q within the shard (-FLT_MAX when the shard cannot offer one).  The caller combines the
- * bounds of all shards (element-wise MAX, e.g. an NCCL all-reduce) and passes the result to phase 2,
- * which rescores only the candidates that can still be in the global top-k and returns this shard's
- * (D, I).  At most 131072 queries per call; filter and finish must be called in pairs with the same
- * nq, xq_dev and k.  Scores are comparable across shards for both metrics. */
-int knn_index_search_filter_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, float* lower_dev, void* stream);
+ * of query q within the shard (-FLT_MAX when the shard cannot offer one), and optionally lower_j_dev[q],
+ * the same for the j-th best (1 <= j <= k; pass NULL to skip).  The caller combines the bounds of all G
+ * shards - element-wise MAX of lower, and with j = ceil(k / G) element-wise MIN of lower_j (every shard holds
+ * j rows at or above it, G*j >= k in total), e.g. two NCCL all-reduces - takes the larger of the two and
+ * passes it to phase 2, which rescores only the candidates that can still be in the global top-k and returns
+ * this shard's (D, I).  At most 131072 queries per call; filter and finish must be called in pairs with the
+ * same nq, xq_dev and k.  Scores are comparable across shards for both metrics. */
+int knn_index_search_filter_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, float* lower_dev, int64_t j,
+                                float* lower_j_dev, void* stream);
 int knn_index_search_finish_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, const float* lower_dev,
                                 float* D_dev, int64_t* I_dev, int64_t id_base, void* stream);
 

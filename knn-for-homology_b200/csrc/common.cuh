@@ -150,6 +150,8 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
 int launch_init_filter(FilterState st, int64_t nq, int64_t nq_pad, int first_count, cudaStream_t s);
 // Two-phase (sharded) search: lower[q] = thr + eps on the way out; thr <- max(thr, lower - eps) on the way in.
 int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* lower, cudaStream_t s);
+// lower_j[q] = (j-th best approximate score in the list) - eps[q]
+int launch_kth_lower(FilterState st, const float* eps, int64_t nq, int j, float* lower_j, cudaStream_t s);
 int launch_apply_lower(float* thr, const float* eps, const float* lower, int64_t nq, cudaStream_t s);
 int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
 

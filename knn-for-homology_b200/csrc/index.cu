@@ -616,7 +616,8 @@ int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, floa
     return KNN_OK;
 }
 
-int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* lower_dev, void* stream) {
+int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* lower_dev, int64_t j,
+                                float* lower_j_dev, void* stream) {
     if (!ix || nq <= 0 || k64 <= 0 || !xq_dev || !lower_dev) {
         set_error("search_filter: invalid arguments");
         return KNN_ERR_INVALID;
@@ -645,6 +646,7 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     ix->last_path = P.tensor ? 2 : 1;
     if (!P.tensor) {  // exact path: nothing to filter, no bound to offer
         KNN_CHECK(launch_fill_f32(lower_dev, nq, -FLT_MAX, s));
+        if (lower_j_dev) KNN_CHECK(launch_fill_f32(lower_j_dev, nq, -FLT_MAX, s));
         P.active = true;
         return KNN_OK;
     }
@@ -662,6 +664,19 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     }
     // lower[q] = thr + eps = (k-th best approximate score) - eps: a lower bound of the true k-th best score
     KNN_CHECK(launch_export_lower(ix->ws2.thr.as<float>(), ix->ws2.eps.as<float>(), nq, lower_dev, s));
+    if (lower_j_dev) {
+        // second bound: (j-th best approximate score) - eps, j <= k.  With G shards and j = ceil(k / G) the MIN of
+        // it over the shards is a lower bound of the global k-th best (every shard holds j rows at or above it).
+        if (j < 1 || j > k) {
+            set_error("search_filter: j must be in [1, k]");
+            return KNN_ERR_INVALID;
+        }
+        for (int64_t b = 0; b < P.nbatches; ++b) {
+            const int64_t q0 = b * P.qb;
+            const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
+            KNN_CHECK(launch_kth_lower(filter_state(ix->ws2, q0, P.cap), ix->ws2.eps.as<float>() + q0, nb, int(j), lower_j_dev + q0, s));
+        }
+    }
     P.active = true;
     return KNN_OK;
 }

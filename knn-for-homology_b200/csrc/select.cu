@@ -459,6 +459,71 @@ tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __
     }
 }
 
+// lower_j[q] = (j-th best approximate score of the list) - eps[q]: at least j rows of this shard have a TRUE
+// score >= lower_j[q].  One warp per query; -FLT_MAX when the list holds fewer than j entries.
+__global__ void __launch_bounds__(256)
+kth_lower_kernel(const float* __restrict__ cand_scores, const int* __restrict__ counts, int cap,
+                 const float* __restrict__ eps, int64_t nq, int j, float* __restrict__ lower_j) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    int cnt = counts[q];
+    cnt = cnt < cap ? cnt : cap;
+    float out = -FLT_MAX;
+    const float e = eps[q];
+    if (cnt >= j && j > 0 && e < FLT_MAX) {
+        const uint32_t kth = warp_kth_largest_mem(cand_scores + q * int64_t(cap), cnt, j, lane);
+        out = from_orderable_f32(kth) - e;
+        if (!(out == out)) out = -FLT_MAX;
+    }
+    if (lane == 0) lower_j[q] = out;
+}
+
+// k-way merge of up to 32 SORTED lists by one warp per query: lane l owns list l and its head; every round the
+// warp takes the best head (64-bit composite keys are distinct, so there are no ties), the owner advances.
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+merge_sorted_lists_kernel(const float* __restrict__ D_lists, const int64_t* __restrict__ I_lists, int nlists, int64_t nq,
+                          int k, int largest, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int64_t base = lane < nlists ? (int64_t(lane) * nq + q) * k : 0;
+    int pos = 0;
+    auto load_key = [&](int p) -> uint64_t {
+        if (lane >= nlists || p >= k) return 0ull;
+        const int64_t id = I_lists[base + p];
+        return make_key(D_lists[base + p], id < 0 ? kInvalidId : uint32_t(id), largest);
+    };
+    uint64_t head = load_key(0);
+    uint64_t next = load_key(1);  // one element of look-ahead hides most of the dependent-load latency
+    for (int r = 0; r < k; ++r) {
+        const uint64_t best = warp_max_u64(head);
+        if (lane == 0) {
+            if (best) {
+                D[q * k + r] = key_score(best, largest);
+                I[q * k + r] = int64_t(key_id(best));
+            } else {
+                D[q * k + r] = largest ? -FLT_MAX : FLT_MAX;
+                I[q * k + r] = -1;
+            }
+        }
+        if (best && head == best) {  // exactly one lane
+            ++pos;
+            head = next;
+            next = load_key(pos + 1);
+        }
+    }
+}
+
 __global__ void export_lower_kernel(const float* __restrict__ thr, const float* __restrict__ eps, int64_t nq,
                                     float* __restrict__ lower) {
     const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -522,6 +587,11 @@ int launch_select_final(const float* list_scores, const uint32_t* list_ids, cons
 int launch_merge_lists(const float* D_lists, const int64_t* I_lists, int nlists, int64_t nq, int k, int largest,
                        float* D, int64_t* I, cudaStream_t s) {
     if (nq <= 0) return KNN_OK;
+    if (nlists <= 32) {  // the inputs are sorted search results: warp tournament instead of a full sort
+        merge_sorted_lists_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(D_lists, I_lists, nlists, nq, k, largest, D, I);
+        KNN_CHECK_LAUNCH();
+        return KNN_OK;
+    }
     merge_lists_kernel<<<unsigned(nq), kSelectThreads, 0, s>>>(D_lists, I_lists, nlists, nq, k, largest, D, I);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
@@ -544,6 +614,12 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
 
 int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* lower, cudaStream_t s) {
     export_lower_kernel<<<unsigned((nq + 255) / 256), 256, 0, s>>>(thr, eps, nq, lower);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_kth_lower(FilterState st, const float* eps, int64_t nq, int j, float* lower_j, cudaStream_t s) {
+    kth_lower_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(st.cand_scores, st.counts, st.cap, eps, nq, j, lower_j);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }

@@ -34,7 +34,7 @@ SIGNATURES = {
     "knn_index_metric": (ctypes.c_int, [c_vp]),
     "knn_index_search": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "knn_index_search_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
-    "knn_index_search_filter_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "knn_index_search_filter_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "knn_index_search_finish_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "knn_index_reconstruct": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
     "knn_merge_topk_dev": (ctypes.c_int, [ctypes.c_int, c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),

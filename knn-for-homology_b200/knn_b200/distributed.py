@@ -118,9 +118,14 @@ class ShardedIndexFlat:
             # filter on every shard -> all-reduce(MAX) of the per-query lower bounds of the k-th best score ->
             # each shard rescoring only what can still be in the global top-k
             xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if as_numpy else x
-            lower = self.local.search_filter(xd, k)
+            # two bounds on the global k-th best true score: the best shard's own k-th, and - every shard holding
+            # j = ceil(k/G) rows at or above its own j-th - the smallest j-th over the shards
+            j = -(-k // self.world)
+            lower, lower_j = self.local.search_filter(xd, k, j)
             mark("filter")
             self._dist.all_reduce(lower, op=self._dist.ReduceOp.MAX, group=self.group)
+            self._dist.all_reduce(lower_j, op=self._dist.ReduceOp.MIN, group=self.group)
+            lower = torch.maximum(lower, lower_j)
             mark("all_reduce_bounds")
             D, I = self.local.search_finish(lower, k)
             mark("finish")

@@ -163,17 +163,21 @@ class IndexFlat:
         return D, I
 
     # -- two-phase search (row-sharded databases; see distributed.ShardedIndexFlat) ----------
-    def search_filter(self, x, k: int):
+    def search_filter(self, x, k: int, j: int | None = None):
         """Phase 1 on CUDA tensor x: returns `lower` (nq,) float32 - per query a lower bound of the true
-        k-th best score inside this shard.  Combine across shards with an element-wise max."""
+        k-th best score inside this shard (combine across shards with an element-wise MAX) - and, when j is
+        given, also `lower_j`, the same for the j-th best (with G shards and j = ceil(k/G), combine with an
+        element-wise MIN: every shard holds j rows at or above it)."""
         import torch
 
         x = self._dev_matrix(x)
         lower = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+        lower_j = torch.empty_like(lower) if j is not None else None
         _lib.check(self._lib.knn_index_search_filter_dev(self._h, x.shape[0], x.data_ptr(), int(k), lower.data_ptr(),
+                                                         int(j or 0), lower_j.data_ptr() if j is not None else None,
                                                          _torch_stream(self.device)))
         self._pending_x = x  # phase 2 needs the same queries (kept alive here)
-        return lower
+        return lower if j is None else (lower, lower_j)
 
     def search_finish(self, lower, k: int, id_base: int = 0):
         """Phase 2: exact rescoring of the candidates that survive the combined bound -> this shard's (D, I)."""
