@@ -231,27 +231,31 @@ scan_f32_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, 
 }
 
 // ---------------------------------------------------------------------------------------
-template <bool BF16DB>
-__device__ __forceinline__ float4 load_row4(const void* __restrict__ xb, uint32_t id, int dp, int c) {
-    if (BF16DB) {
-        uint2 p = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xb) + int64_t(id) * dp)[c];
-        float2 lo = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.x));
-        float2 hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&p.y));
-        return make_float4(lo.x, lo.y, hi.x, hi.y);
-    }
-    return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(xb) + int64_t(id) * dp) + c);
+// A 4-element chunk of a database row as it lies in memory: the raw loads of a row are issued back to back and
+// only converted when the FMAs consume them (a conversion next to its load makes every load wait for the previous one).
+template <bool BF16DB> struct RowChunk { using T = float4; };
+template <> struct RowChunk<true> { using T = uint2; };
+
+__device__ __forceinline__ float4 chunk_to_f32(const float4& v) { return v; }
+__device__ __forceinline__ float4 chunk_to_f32(const uint2& p) {
+    // bf16 -> fp32 is a 16-bit shift
+    return make_float4(__uint_as_float(p.x << 16), __uint_as_float(p.x & 0xFFFF0000u), __uint_as_float(p.y << 16),
+                       __uint_as_float(p.y & 0xFFFF0000u));
 }
 
 // One CTA per query, the query row in shared memory.  Each warp takes 32 list entries at a time with one
-// coalesced load, then walks the entries that passed the final threshold two at a time: the 16 independent
-// 16-byte loads per lane of two database rows are in flight before the FMAs consume them.  The FMA order per
-// (row, query) pair is the scan kernel's, so a pair gets the same bits whichever path scored it.
+// coalesced load, then walks the entries that passed the final threshold NR at a time (2 fp32 rows or 4 bf16
+// rows: 8 KB in flight per warp either way): all loads of the NR rows are issued before the FMAs consume them.
+// The FMA order per (row, query) pair is the scan kernel's, so a pair gets the same bits whichever path scored it.
 template <bool BF16DB>
 __global__ void __launch_bounds__(kBlock)
 rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, int dp, const void* __restrict__ xb,
               const float* __restrict__ ynorm2, int metric, float* __restrict__ cand_scores,
               uint32_t* __restrict__ cand_ids, const int* __restrict__ counts, const float* __restrict__ tau,
               int cap) {
+    using Raw = typename RowChunk<BF16DB>::T;
+    constexpr int NR = BF16DB ? 4 : 2;
+    constexpr int U = 8;  // chunks per lane and row in flight
     extern __shared__ float4 sq[];  // [dp/4]
     const int64_t q = blockIdx.x;
     const int dp4 = dp / 4;
@@ -266,6 +270,9 @@ rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, in
     float* cs = cand_scores + q * int64_t(cap);
     uint32_t* ci = cand_ids + q * int64_t(cap);
     const float xn = metric == KNN_METRIC_L2 ? xnorm2[q] : 0.f;
+    const Raw* rows = static_cast<const Raw*>(xb);
+    Raw zero;
+    memset(&zero, 0, sizeof(zero));
     for (int base = warp * 32; base < cnt; base += kWarpsPerBlock * 32) {
         const int i = base + lane;
         float approx = 0.f;
@@ -278,48 +285,56 @@ rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, in
         unsigned mask = __ballot_sync(0xffffffffu, valid);
         float res = 0.f;
         while (mask) {  // warp-uniform
-            const int j0 = __ffs(int(mask)) - 1;
-            mask &= mask - 1;
-            const bool two = mask != 0;
-            const int j1 = two ? __ffs(int(mask)) - 1 : j0;
-            mask &= mask - 1;  // no-op when mask is already 0
-            const uint32_t id0 = __shfl_sync(0xffffffffu, id, j0);
-            const uint32_t id1 = __shfl_sync(0xffffffffu, id, j1);
-            float a0 = 0.f, a1 = 0.f;
-            for (int c0 = lane; c0 < dp4; c0 += 8 * 32) {
-                float4 y0[8], y1[8];
+            int src[NR];
+            uint32_t rid[NR];
+            const Raw* rp[NR];
+            int n = 0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+            for (int r = 0; r < NR; ++r) {
+                src[r] = mask ? __ffs(int(mask)) - 1 : 0;
+                n += mask ? 1 : 0;
+                mask &= mask - 1;  // no-op when mask is already 0
+                rid[r] = __shfl_sync(0xffffffffu, id, src[r]);
+                rp[r] = rows + int64_t(rid[r]) * dp4;
+            }
+            float acc[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = 0.f;
+            for (int c0 = lane; c0 < dp4; c0 += U * 32) {
+                Raw y[NR][U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
                     const int c = c0 + u * 32;
-                    if (c < dp4) {
-                        y0[u] = load_row4<BF16DB>(xb, id0, dp, c);
-                        if (two) y1[u] = load_row4<BF16DB>(xb, id1, dp, c);
-                    }
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) y[r][u] = (c < dp4 && r < n) ? __ldg(rp[r] + c) : zero;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int c = c0 + u * 32;
                     if (c < dp4) {
                         const float4 qv = sq[c];
-                        a0 = fmaf(y0[u].x, qv.x, a0); a0 = fmaf(y0[u].y, qv.y, a0);
-                        a0 = fmaf(y0[u].z, qv.z, a0); a0 = fmaf(y0[u].w, qv.w, a0);
-                        if (two) {
-                            a1 = fmaf(y1[u].x, qv.x, a1); a1 = fmaf(y1[u].y, qv.y, a1);
-                            a1 = fmaf(y1[u].z, qv.z, a1); a1 = fmaf(y1[u].w, qv.w, a1);
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            const float4 yv = chunk_to_f32(y[r][u]);
+                            float a = acc[r];
+                            a = fmaf(yv.x, qv.x, a); a = fmaf(yv.y, qv.y, a);
+                            a = fmaf(yv.z, qv.z, a); a = fmaf(yv.w, qv.w, a);
+                            acc[r] = a;
                         }
                     }
                 }
             }
-            a0 = warp_sum(a0);
-            a1 = warp_sum(a1);
-            if (metric == KNN_METRIC_L2) {
-                a0 = xn + ynorm2[id0] - 2.0f * a0;
-                a0 = a0 < 0.f ? 0.f : a0;
-                a1 = xn + ynorm2[id1] - 2.0f * a1;
-                a1 = a1 < 0.f ? 0.f : a1;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                float a = warp_sum(acc[r]);
+                if (r < n) {
+                    if (metric == KNN_METRIC_L2) {
+                        a = xn + ynorm2[rid[r]] - 2.0f * a;
+                        a = a < 0.f ? 0.f : a;
+                    }
+                    if (lane == src[r]) res = a;
+                }
             }
-            if (lane == j0) res = a0;
-            if (two && lane == j1) res = a1;
         }
         if (i < cnt) {
             if (valid) cs[i] = res;
