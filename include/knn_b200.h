@@ -110,6 +110,53 @@ int knn_index_reconstruct(knn_index* idx, int64_t i0, int64_t n, float* out);
 int knn_merge_topk_dev(int metric, int64_t nq, int64_t k, int nlists, const float* D_lists_dev,
                        const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev, void* stream);
 
+/* ---- Downstream of search: what the reference does with (D, I) next. ----
+ * All pointers are device pointers; I is the (nq,k) int64 matrix index.search returned, D its float32 scores.
+ * Label gathers keep Python/numpy index semantics: a negative id counts from the end (id -1 -> last row).
+ * `err_dev` is a caller-zeroed int the kernels OR flags into: 1 = NaN score where the reference raises
+ * ValueError, 2 = id out of range (IndexError), 4 = infinite score with clip = 0 (OverflowError). */
+
+/* seqvec_search/main.py:53-82 (evaluate_faiss + evaluate): lead[q] = length of the leading run of hits whose
+ * family equals the query's (AUC1 numerator), tp[q] = number of such hits (TP numerator).  The common
+ * denominator, the family's size in the database (main.py:68), is a bincount the caller does once. */
+int knn_eval_family_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int32_t* query_family_dev,
+                        const int32_t* db_family_dev, int64_t n_db, int32_t* lead_dev, int32_t* tp_dev, int* err_dev,
+                        void* stream);
+
+/* cath/cath.py:76-84 (compute_is_correct), all-vs-all: out[q][l][h] = mapping[q][l] == mapping[I[q][h]][l],
+ * mapping = (n_db, levels) int32 label codes, out = (nq, levels, k) bytes. */
+int knn_eval_levels_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int32_t* mapping_dev, int levels, int64_t n_db,
+                        uint8_t* out_dev, int* err_dev, void* stream);
+
+/* pfam/proteins.py:201-207 (compute_correctness_array) and pfam/proteins_shared.py:139-157 (compute_auc1):
+ * per-query sets of homologous database rows in CSR form (set_offsets (nq+1), members sorted ascending within a
+ * set).  correct[q][h] = I[q][h] in set q (plain value membership); lead[q] = leading run of member hits, ids
+ * wrapped by n_db_wrap first when it is > 0 (target_ids[hit]).  Either output may be NULL. */
+int knn_eval_sets_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int64_t* set_offsets_dev,
+                      const int64_t* set_members_dev, int64_t n_db_wrap, uint8_t* correct_dev, int32_t* lead_dev,
+                      void* stream);
+
+/* pfam/proteins.py:85-122 (remove_self_hit), in place: the first occurrence of self_ids[q] (q itself when
+ * self_ids_dev is NULL) in row q - or the last column when it is absent, counted in *n_missing_dev - is rotated
+ * to column 0; the caller then drops column 0 (cath/search.py:26 drops it blindly).  D_dev may be NULL. */
+int knn_remove_self_hit_dev(int64_t nq, int64_t k, int64_t* I_dev, float* D_dev, const int64_t* self_ids_dev,
+                            uint64_t* n_missing_dev, void* stream);
+
+/* seqvec_search/mmseqs/_write_prefilter_db.py:52-97 (write_prefilter_db): the text of the MMseqs2 prefilter
+ * database.  Data file: per query, one line "<train_map[hit]>\t<int(clip(score,-1e30,1e30)*100)>\t0\n" per hit
+ * != -1 (float32 arithmetic, truncation toward zero, exact for every finite value), then a NUL.  Index file: per
+ * query "<test_map[queries[q]]>\t<offset>\t<length>\n" (queries_dev NULL = 0..nq-1).
+ * measure: sec_off_dev[0..nq] = byte offset of every query's section (sec_off[nq] = data file size),
+ *          idx_off_dev[0..nq] likewise for the index lines.
+ * emit:    writes both texts into caller buffers of those sizes (data_dev 16-byte aligned). */
+int knn_prefilter_measure_dev(int64_t nq, int64_t k, const int64_t* I_dev, const float* D_dev, const int64_t* queries_dev,
+                              const int64_t* test_map_dev, int64_t n_test, const int64_t* train_map_dev, int64_t n_train,
+                              int clip, int64_t* sec_off_dev, int64_t* idx_off_dev, int* err_dev, void* stream);
+int knn_prefilter_emit_dev(int64_t nq, int64_t k, const int64_t* I_dev, const float* D_dev, const int64_t* queries_dev,
+                           const int64_t* test_map_dev, int64_t n_test, const int64_t* train_map_dev, int64_t n_train,
+                           int clip, const int64_t* sec_off_dev, const int64_t* idx_off_dev, uint8_t* data_dev,
+                           uint8_t* index_dev, int* err_dev, void* stream);
+
 /* Tuning / introspection.  Parameters: "path" (0 auto, 1 exact fp32 scan, 2 tensor-core
  * filter + rerank), "query_batch", "profile" (1: time the dominant kernel with CUDA events),
  * "cta_group" (tcgen05 cta_group of the GEMM kernel, 1 or 2), "tensor_min_nq", "tensor_min_n".

@@ -38,6 +38,14 @@ SIGNATURES = {
     "knn_index_search_finish_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "knn_index_reconstruct": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
     "knn_merge_topk_dev": (ctypes.c_int, [ctypes.c_int, c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "knn_eval_family_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "knn_eval_levels_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
+    "knn_eval_sets_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "knn_remove_self_hit_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "knn_prefilter_measure_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, ctypes.c_int,
+                                                 c_vp, c_vp, c_vp, c_vp]),
+    "knn_prefilter_emit_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, ctypes.c_int,
+                                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "knn_index_set_param": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "knn_index_get_stat": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
 }
