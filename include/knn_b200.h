@@ -110,6 +110,23 @@ int knn_index_reconstruct(knn_index* idx, int64_t i0, int64_t n, float* out);
 int knn_merge_topk_dev(int metric, int64_t nq, int64_t k, int nlists, const float* D_lists_dev,
                        const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev, void* stream);
 
+/* Cross-shard exchange fused with the merge, over NVLink peer memory (new).  One process
+ * per GPU: every rank allocates an exchange buffer (plain cudaMalloc, so it can be exported), publishes its
+ * 64-byte CUDA IPC handle to the other ranks (any transport: a host collective, a file, MPI) and maps theirs.
+ * knn_merge_topk_peer_dev then merges queries [q0, q1) - this rank's slice - reading rank l's sorted per-shard
+ * (D, I) rows through D_peer[l] / I_peer[l] (layout [nq][k], global ids) and storing the merged rows into every
+ * rank's D_out_peer[l] / I_out_peer[l].  The pointer arrays are HOST arrays of `nranks` device pointers valid on
+ * the calling device (own buffer or mapped peers).  The caller orders it between two barriers: all per-shard
+ * results written before, all ranks' merge kernels finished before anyone reads its output. */
+int knn_peer_buffer_alloc(void** dev_ptr_out, int64_t bytes, int device);
+int knn_peer_buffer_free(void* dev_ptr);
+int knn_peer_handle_get(const void* dev_ptr, unsigned char* handle64);
+int knn_peer_handle_open(const unsigned char* handle64, int device, void** dev_ptr_out);
+int knn_peer_handle_close(void* dev_ptr);
+int knn_merge_topk_peer_dev(int metric, int64_t nq, int64_t k, int nranks, int64_t q0, int64_t q1,
+                            const void* const* D_peer, const void* const* I_peer, void* const* D_out_peer,
+                            void* const* I_out_peer, void* stream);
+
 /* ---- Downstream of search: what the reference does with (D, I) next. ----
  * All pointers are device pointers; I is the (nq,k) int64 matrix index.search returned, D its float32 scores.
  * Label gathers keep Python/numpy index semantics: a negative id counts from the end (id -1 -> last row).

@@ -38,6 +38,12 @@ SIGNATURES = {
     "knn_index_search_finish_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "knn_index_reconstruct": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
     "knn_merge_topk_dev": (ctypes.c_int, [ctypes.c_int, c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "knn_peer_buffer_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i64, ctypes.c_int]),
+    "knn_peer_buffer_free": (ctypes.c_int, [c_vp]),
+    "knn_peer_handle_get": (ctypes.c_int, [c_vp, c_vp]),
+    "knn_peer_handle_open": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "knn_peer_handle_close": (ctypes.c_int, [c_vp]),
+    "knn_merge_topk_peer_dev": (ctypes.c_int, [ctypes.c_int, c_i64, c_i64, ctypes.c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "knn_eval_family_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "knn_eval_levels_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
     "knn_eval_sets_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),

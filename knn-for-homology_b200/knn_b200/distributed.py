@@ -15,6 +15,121 @@ from __future__ import annotations
 import numpy as np
 
 
+class _DeviceBytes:
+    """A raw device allocation presented to torch through the CUDA array interface (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """Exchange buffers of all ranks of one box, mapped into every rank with CUDA IPC (NVLink peer memory).
+
+    Each rank owns one cudaMalloc'ed buffer laid out [I_local | I_merged | D_local | D_merged] for the current
+    (nq, k); ``tables`` gives, per region, a host array with the address of that region in every rank's buffer
+    as seen from THIS rank.  All methods are collective over ``group``."""
+
+    def __init__(self, dist, group, rank: int, world: int, device: int):
+        import torch
+
+        from . import _lib
+
+        self._dist, self.group, self.rank, self.world, self.device = dist, group, rank, world, device
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.capacity = 0
+        self.own = None          # ctypes.c_void_p
+        self.bases = []          # address of every rank's buffer in this process
+        self._own_tensor = None
+        backend = dist.get_backend(group)
+        self._stream_ordered = backend == "nccl"
+        self._token = torch.zeros(1, device=torch.device("cuda", device)) if self._stream_ordered else None
+
+    def barrier(self) -> None:
+        """Everything enqueued before it on every rank happens before anything enqueued after it on any rank."""
+        import torch
+
+        if self._stream_ordered:
+            self._dist.all_reduce(self._token, group=self.group)  # on the current stream, no host sync
+        else:
+            torch.cuda.synchronize(self.device)
+            self._dist.barrier(group=self.group)
+
+    def _release(self) -> None:
+        import ctypes
+
+        if self.own is None:
+            return
+        self.barrier()
+        import torch
+
+        torch.cuda.synchronize(self.device)
+        for r, b in enumerate(self.bases):
+            if r != self.rank:
+                self._check(self._lib.knn_peer_handle_close(ctypes.c_void_p(b)))
+        self._dist.barrier(group=self.group)  # nobody maps the buffer any more
+        self._check(self._lib.knn_peer_buffer_free(self.own))
+        self.own, self.bases, self._own_tensor, self.capacity = None, [], None, 0
+
+    def ensure(self, nbytes: int) -> None:
+        import ctypes
+
+        import torch
+
+        if nbytes <= self.capacity:
+            return
+        self._release()
+        cap = 1 << 20
+        while cap < nbytes:
+            cap *= 2
+        own = ctypes.c_void_p()
+        self._check(self._lib.knn_peer_buffer_alloc(ctypes.byref(own), cap, self.device))
+        handle = (ctypes.c_ubyte * 64)()
+        self._check(self._lib.knn_peer_handle_get(own, handle))
+        handles = [None] * self.world
+        self._dist.all_gather_object(handles, bytes(handle), group=self.group)
+        bases = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                bases.append(own.value)
+            else:
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                self._check(self._lib.knn_peer_handle_open(buf, self.device, ctypes.byref(p)))
+                bases.append(p.value)
+        self.own, self.bases, self.capacity = own, bases, cap
+        self._own_tensor = torch.as_tensor(_DeviceBytes(own.value, cap), device=torch.device("cuda", self.device))
+
+    @staticmethod
+    def layout(nq: int, k: int):
+        n = nq * k
+        return {"I_local": 0, "I_merged": 8 * n, "D_local": 16 * n, "D_merged": 20 * n, "bytes": 24 * n}
+
+    def views(self, nq: int, k: int):
+        """torch views of this rank's own regions."""
+        import torch
+
+        lay = self.layout(nq, k)
+        n = nq * k
+        t = self._own_tensor
+
+        def region(name, dtype, size):
+            return t[lay[name]:lay[name] + n * size].view(dtype).view(nq, k)
+
+        return (region("D_local", torch.float32, 4), region("I_local", torch.int64, 8),
+                region("D_merged", torch.float32, 4), region("I_merged", torch.int64, 8))
+
+    def tables(self, nq: int, k: int):
+        import ctypes
+
+        lay = self.layout(nq, k)
+        arr = lambda name: (ctypes.c_void_p * self.world)(*[b + lay[name] for b in self.bases])  # noqa: E731
+        return arr("D_local"), arr("I_local"), arr("D_merged"), arr("I_merged")
+
+    def close(self) -> None:
+        self._release()
+
+
 def shard_bounds(n: int, world: int):
     """Contiguous near-equal row ranges: rank r owns [b[r], b[r+1])."""
     return [(n * r) // world for r in range(world + 1)]
@@ -24,7 +139,7 @@ class ShardedIndexFlat:
     TWO_PHASE_MAX_QUERIES = 131072  # limit of knn_index_search_filter_dev (candidate lists stay resident)
 
     def __init__(self, d: int, metric: int, group=None, device=None, index_factory=None, merge_fn=None,
-                 exchange_bounds: bool = True, **index_kw):
+                 exchange_bounds: bool = True, peer_merge: bool = True, **index_kw):
         import torch.distributed as dist
 
         self._dist = dist
@@ -43,6 +158,8 @@ class ShardedIndexFlat:
 
             merge_fn = merge_topk
         self.exchange_bounds = exchange_bounds
+        self.peer_merge = peer_merge  # exchange + merge in one kernel over NVLink peer memory (CUDA results only)
+        self._exchange = None
         self.profile_phases = False
         self.last_phases_ms = None
         self.local = index_factory()
@@ -139,7 +256,10 @@ class ShardedIndexFlat:
                     D, I = D.to(dev), I.to(dev)
         I = self._to_global(I)
         mark("to_global")
-        if self.world > 1:
+        if self.world > 1 and self.peer_merge and D.is_cuda and self.world <= 16 and (self.world + 1) * k * 8 <= 200 * 1024:
+            D, I = self._merge_over_peer_memory(D, I)
+            mark("peer_merge")
+        elif self.world > 1:
             nq, kk = D.shape
             Dg = torch.empty((self.world * nq, kk), dtype=D.dtype, device=D.device)
             Ig = torch.empty((self.world * nq, kk), dtype=I.dtype, device=I.device)
@@ -154,3 +274,25 @@ class ShardedIndexFlat:
         if as_numpy:
             return D.cpu().numpy(), I.cpu().numpy()
         return D, I
+
+    def _merge_over_peer_memory(self, D, I):
+        """This rank merges its slice of the queries out of the peers' memory and stores the merged rows into every
+        rank's buffer (knn_merge_topk_peer_dev); two barriers order it against the per-shard searches and the readers."""
+        from . import _lib
+        from .index import _torch_stream
+
+        nq, k = D.shape
+        if self._exchange is None:
+            self._exchange = PeerExchange(self._dist, self.group, self.rank, self.world, D.device.index)
+        ex = self._exchange
+        ex.ensure(ex.layout(nq, k)["bytes"])
+        D_loc, I_loc, D_out, I_out = ex.views(nq, k)
+        D_loc.copy_(D)
+        I_loc.copy_(I)
+        ex.barrier()  # every shard's results are in place
+        b = shard_bounds(nq, self.world)
+        tD, tI, tDo, tIo = ex.tables(nq, k)
+        _lib.check(_lib.load().knn_merge_topk_peer_dev(self.metric_type, nq, k, self.world, b[self.rank], b[self.rank + 1],
+                                                       tD, tI, tDo, tIo, _torch_stream(D.device.index)))
+        ex.barrier()  # every rank's slice has landed in this rank's buffer
+        return D_out.clone(), I_out.clone()
