@@ -216,7 +216,20 @@ class ShardedIndexFlat:
 
     def search(self, x, k: int):
         """Returns the merged (D, I) on every rank (torch tensors on the local index's device, or
-        numpy arrays when x is numpy)."""
+        numpy arrays when x is numpy).  Calls with more queries than the two-phase search keeps resident
+        (TWO_PHASE_MAX_QUERIES) are processed in chunks of that size (config C5: 1M queries)."""
+        n = x.shape[0]
+        if n > self.TWO_PHASE_MAX_QUERIES and self.world > 1:
+            step = self.TWO_PHASE_MAX_QUERIES
+            parts = [self._search_chunk(x[i:i + step], k) for i in range(0, n, step)]
+            if isinstance(x, np.ndarray):
+                return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+            import torch
+
+            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        return self._search_chunk(x, k)
+
+    def _search_chunk(self, x, k: int):
         import torch
 
         as_numpy = isinstance(x, np.ndarray)

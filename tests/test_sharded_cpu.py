@@ -70,6 +70,10 @@ def _worker(rank, world, port, metric, out):
         D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
         assert np.array_equal(I, I_ref), (rank, k)
         assert np.array_equal(D, D_ref), (rank, k)
+    index.TWO_PHASE_MAX_QUERIES = 5  # more queries than one two-phase call holds: processed in chunks (17 = 5+5+5+2)
+    D, I = index.search(xq, 7)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 7, metric)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)
     if rank == 0:
         Path(out).write_text("ok")
     dist.destroy_process_group()
