@@ -73,7 +73,8 @@ def _worker(rank, world, port, metric, out):
     index.TWO_PHASE_MAX_QUERIES = 5  # more queries than one two-phase call holds: processed in chunks (17 = 5+5+5+2)
     D, I = index.search(xq, 7)
     D_ref, I_ref = fo.knn_flat(xq, xb, 7, metric)
-    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)
+    # (the oracle's sgemm rounds differently for a different batch shape: scores to fp32 noise, ids exact)
+    assert np.array_equal(I, I_ref) and np.allclose(D, D_ref, rtol=1e-6, atol=1e-6)
     if rank == 0:
         Path(out).write_text("ok")
     dist.destroy_process_group()
