@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cta-group", type=int, default=2, choices=[1, 2], help="tcgen05 cta_group of the GEMM kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-phases", action="store_true", help="skip the extra untimed pass that times the phases of the sharded search")
+    ap.add_argument("--bf16-storage", action="store_true", help="the bf16 values ARE the database (config C5): no fp32 master rows")
     return ap.parse_args()
 
 
@@ -150,8 +152,11 @@ def reference_arm(args, rank, world):
 
 def workload_config(args, world):
     name = "C4" if (args.nb, args.nq, args.k) == (10_000_000, 100_000, 100) else "custom"
-    return {"workload": f"{name}: synthetic normalised {args.nb}x{D_DIM} fp32 database, {args.nq} queries, k={args.k}, "
-                        f"inner product, exact (ids = fp32 IndexFlatIP)",
+    if (args.nb, args.nq, args.k, args.bf16_storage) == (100_000_000, 1_000_000, 1000, True):
+        name = "C5"
+    store = "bf16" if args.bf16_storage else "fp32"
+    return {"workload": f"{name}: synthetic normalised {args.nb}x{D_DIM} {store} database, {args.nq} queries, k={args.k}, "
+                        f"inner product, exact (ids = fp32 IndexFlatIP on the stored values)",
             "database_rows": args.nb, "queries_per_step": args.nq, "k": args.k, "d": D_DIM,
             "sharding": f"rows over {world} GPU(s)", "l2": "inputs larger than L2 (bf16 database shard >> 126 MB)"}
 
@@ -179,7 +184,7 @@ def main():
 
     # ---- build the database shard on the device (index build is reported, not timed as search) ----
     t_build = time.perf_counter()
-    index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank)
+    index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank, bf16_storage=args.bf16_storage)
     b = shard_bounds(args.nb, world)
     lo, hi = b[rank], b[rank + 1]
     index.local.set_param("cta_group", args.cta_group)
@@ -198,10 +203,11 @@ def main():
     g = torch.Generator(device=dev).manual_seed(4321)
     xq_dev = torch.randn(args.nq, D_DIM, device=dev, generator=g)
     knn_b200.normalize_L2(xq_dev)
-    xq_host = torch.empty((args.nq, D_DIM), dtype=torch.float32, pin_memory=True)
-    xq_host.copy_(xq_dev)
-    D_host = torch.empty((args.nq, args.k), dtype=torch.float32, pin_memory=True)
-    I_host = torch.empty((args.nq, args.k), dtype=torch.int64, pin_memory=True)
+    if not args.no_e2e:
+        xq_host = torch.empty((args.nq, D_DIM), dtype=torch.float32, pin_memory=True)
+        xq_host.copy_(xq_dev)
+        D_host = torch.empty((args.nq, args.k), dtype=torch.float32, pin_memory=True)
+        I_host = torch.empty((args.nq, args.k), dtype=torch.int64, pin_memory=True)
     torch.cuda.synchronize()
 
     lib = knn_b200._lib.load()
@@ -211,8 +217,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = {}
+
     def step_device():
-        return index.search(xq_dev, args.k)
+        last["DI"] = index.search(xq_dev, args.k)
+        return last["DI"]
 
     def step_e2e():
         if world == 1:
@@ -238,8 +247,8 @@ def main():
         for _ in range(steps):
             fn()
             if profile:
-                gemm_ms += index.local.stat("gemm_ms")
-                gemm_launches += int(index.local.stat("gemm_launches"))
+                gemm_ms += index.last_stats["gemm_ms"]
+                gemm_launches += int(index.last_stats["gemm_launches"])
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -266,7 +275,7 @@ def main():
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps}
 
     # parity spot check inside the bench: a few queries rescored exhaustively by the exact fp32 path
-    D, I = step_device()
+    D, I = last["DI"]  # result of the last timed step
     search_path = int(index.local.stat("path"))
     chk = torch.arange(0, args.nq, max(1, args.nq // 64), device=dev)[:64]
     index.local.set_param("path", 1)
@@ -275,7 +284,7 @@ def main():
     parity_ok = bool(torch.equal(I[chk], I1) and torch.equal(D[chk], D1))
 
     phases = None
-    if world > 1:  # one extra, untimed step with CUDA events around the phases of the sharded search
+    if world > 1 and not args.no_phases:  # one extra, untimed step with CUDA events around the phases of the sharded search
         index.profile_phases = True
         step_device()
         index.profile_phases = False

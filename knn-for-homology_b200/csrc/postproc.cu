@@ -167,14 +167,29 @@ remove_self_hit_kernel(int64_t* I, float* D, int64_t nq, int k,
 // per query one index line "<test_map[query]>\t<offset>\t<length>\n".
 typedef unsigned __int128 u128;
 
+__device__ __forceinline__ int dec_digits_u32(uint32_t v) {
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+         : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
 __device__ __forceinline__ int dec_digits_u64(unsigned long long v) {
-    int n = 1;
-    while (v >= 10000ull) { v /= 10000ull; n += 4; }
+    if (v < 4294967296ull) return dec_digits_u32(uint32_t(v));  // ids and cosine scores live here: 32-bit arithmetic only
+    int n = 9;
+    v /= 1000000000ull;
     while (v >= 10ull) { v /= 10ull; ++n; }
-    return n;
+    return n + 1;
 }
 // writes the decimal digits of v so that the last one lands at end[-1]; returns the number written
+__device__ __forceinline__ int put_u32(uint8_t* end, uint32_t v) {
+    int n = 0;
+    do {
+        *--end = uint8_t('0' + v % 10u);
+        v /= 10u;
+        ++n;
+    } while (v);
+    return n;
+}
 __device__ __forceinline__ int put_u64(uint8_t* end, unsigned long long v) {
+    if (v < 4294967296ull) return put_u32(end, uint32_t(v));
     int n = 0;
     do {
         *--end = uint8_t('0' + v % 10ull);
@@ -203,11 +218,17 @@ __device__ __forceinline__ BigInt trunc_f32(float v) {
     return b;
 }
 __device__ __forceinline__ int dec_len(const BigInt& b) {
+    if ((b.mag >> 64) == 0) return (b.neg ? 1 : 0) + dec_digits_u64((unsigned long long)b.mag);  // no 128-bit division
     const unsigned long long hi = (unsigned long long)(b.mag / kTen19);
     const unsigned long long lo = (unsigned long long)(b.mag % kTen19);
     return (b.neg ? 1 : 0) + (hi ? dec_digits_u64(hi) + 19 : dec_digits_u64(lo));
 }
 __device__ __forceinline__ void put_big(uint8_t* end, const BigInt& b, int len) {
+    if ((b.mag >> 64) == 0) {
+        end -= put_u64(end, (unsigned long long)b.mag);
+        if (b.neg) *--end = '-';
+        return;
+    }
     const unsigned long long hi = (unsigned long long)(b.mag / kTen19);
     unsigned long long lo = (unsigned long long)(b.mag % kTen19);
     if (hi) {

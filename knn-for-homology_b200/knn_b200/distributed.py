@@ -162,6 +162,7 @@ class ShardedIndexFlat:
         self._exchange = None
         self.profile_phases = False
         self.last_phases_ms = None
+        self.last_stats = None
         self.local = index_factory()
         self._merge = merge_fn
         # one (global_start, local_start, count) triple per add() call
@@ -221,13 +222,22 @@ class ShardedIndexFlat:
         n = x.shape[0]
         if n > self.TWO_PHASE_MAX_QUERIES and self.world > 1:
             step = self.TWO_PHASE_MAX_QUERIES
-            parts = [self._search_chunk(x[i:i + step], k) for i in range(0, n, step)]
+            parts, acc = [], {"gemm_ms": 0.0, "gemm_launches": 0.0}
+            for i in range(0, n, step):
+                parts.append(self._search_chunk(x[i:i + step], k))
+                if hasattr(self.local, "stat"):  # per-call statistics of the shard engine, summed over the chunks
+                    for name in acc:
+                        acc[name] += self.local.stat(name)
+            self.last_stats = acc
             if isinstance(x, np.ndarray):
                 return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
             import torch
 
             return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
-        return self._search_chunk(x, k)
+        out = self._search_chunk(x, k)
+        self.last_stats = ({name: self.local.stat(name) for name in ("gemm_ms", "gemm_launches")}
+                           if hasattr(self.local, "stat") else None)
+        return out
 
     def _search_chunk(self, x, k: int):
         import torch
