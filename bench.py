@@ -235,6 +235,8 @@ def main():
                 I_host.copy_(I, non_blocking=True)
             torch.cuda.synchronize()
 
+    by_rank = {}
+
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
             fn()
@@ -256,6 +258,10 @@ def main():
         index.local.set_param("profile", 0)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
+            per_rank = torch.zeros((world, 2), device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(per_rank, torch.tensor([ms, gemm_ms], device=dev, dtype=torch.float64))
+            by_rank["step_ms"] = [round(v / steps, 3) for v in per_rank[:, 0].tolist()]
+            by_rank["gemm_ms"] = [round(v / steps, 3) for v in per_rank[:, 1].tolist()]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches, gemm_ms, gemm_launches
 
@@ -265,6 +271,7 @@ def main():
     ms, launches, gemm_ms, gemm_launches = timed(step_device, args.steps, args.warmup, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     value = args.nq * args.steps / (ms / 1e3)
+    by_rank_value = dict(by_rank)  # per-rank step / GEMM time of the `value` leg (chip-to-chip spread under the power cap)
 
     e2e = None
     if not args.no_e2e:
@@ -317,7 +324,7 @@ def main():
             "data": "synthetic",
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
-            "search_path": search_path, "cta_group": args.cta_group, "phases_ms_rank0": phases,
+            "search_path": search_path, "cta_group": args.cta_group, "phases_ms_rank0": phases, "ms_per_step_by_rank": by_rank_value or None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
