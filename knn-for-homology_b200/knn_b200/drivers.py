@@ -1,0 +1,127 @@
+"""The reference's driver functions around the flat search, with the
+same names, arguments, return values and files - but ONE upload of the embeddings: normalisation,
+index build and search all run on the device copy, where the reference (and a plain faiss alias)
+crosses the host/device boundary for every step (normalize_L2: up and down, add: up, search: up).
+
+  search            cath/search.py:13-26
+  search_and_save   cath/search.py:29-53
+  faiss_search      seqvec_search/main.py:22-50
+  proteins_search   pfam/proteins_search.py:11-57 (flat branch)
+
+Results are bit-identical to calling the faiss-style API step by step (same kernels, same order).
+"""
+from __future__ import annotations
+
+import time
+from pathlib import Path
+
+import numpy as np
+
+from .index import METRIC_INNER_PRODUCT, METRIC_L2, IndexFlat, _default_device, normalize_L2
+from .io import write_index
+
+
+def _upload(x: np.ndarray, device: int):
+    import torch
+
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    return torch.from_numpy(x).to(torch.device("cuda", device))
+
+
+def search(embeddings: np.ndarray, hits: int = 10, metric: int = METRIC_INNER_PRODUCT, device: int | None = None):
+    """All-vs-all search; one more hit is searched internally because the first one is the self hit
+    (cath/search.py:16).  The caller's array is not modified (the reference normalises a copy)."""
+    device = _default_device() if device is None else device
+    x = _upload(embeddings, device)
+    if metric == METRIC_INNER_PRODUCT:
+        normalize_L2(x)
+    index = IndexFlat(x.shape[1], metric, device=device)
+    index.add(x)
+    scores, results = index.search(x, hits + 1)
+    scores, results = scores.cpu().numpy(), results.cpu().numpy()
+    # Remove the self hit (blindly column 0, like cath/search.py:26)
+    return results[:, 1:], scores[:, 1:]
+
+
+def search_and_save(cath_data: Path, device: int | None = None) -> None:
+    """cath/search.py:29-53: both metrics over every *.npy of the directory; writes
+    `<stem>.<metric>-search-time.txt`, `hits_<metric>.npz` and `scores_<metric>.npz`."""
+    cath_data = Path(cath_data)
+    for name, metric in [("Cosine", METRIC_INNER_PRODUCT), ("Euclidean", METRIC_L2)]:
+        print(f"Searching with {name}")
+        hits, scores = {}, {}
+        for file_path in sorted(cath_data.glob("*.npy")):
+            # fp16 embeddings of the half precision model are cast to the fp32 the index wants (cath/search.py:39-40)
+            embeddings = np.load(file_path).astype(np.float32)
+            print(file_path.stem, embeddings.shape)
+            start = time.time()
+            hits[file_path.stem], scores[file_path.stem] = search(embeddings, metric=metric, device=device)
+            end = time.time()
+            print(end - start)
+            cath_data.joinpath(file_path.with_suffix(f".{name.lower()}-search-time.txt")).write_text(str(end - start))
+        np.savez(cath_data.joinpath(f"hits_{name.lower()}.npz"), **hits)
+        np.savez(cath_data.joinpath(f"scores_{name.lower()}.npz"), **scores)
+
+
+def faiss_search(haystack, queries: np.ndarray, hits: int = 13, metric: int = METRIC_INNER_PRODUCT, device: int | None = None):
+    """seqvec_search/main.py:22-50.  ``haystack`` is a matrix or a ready index.  Returns
+    ``(ids, scores, search_seconds)`` - ids first.  Like the reference, queries (and a matrix
+    haystack) are L2-normalised IN PLACE for the inner-product metric."""
+    device = _default_device() if device is None else device
+    q = _upload(queries, device)
+    if metric == METRIC_INNER_PRODUCT:
+        normalize_L2(q)
+        _write_back(queries, q)
+    if isinstance(haystack, np.ndarray):
+        h = _upload(haystack, device)
+        if metric == METRIC_INNER_PRODUCT:
+            normalize_L2(h)
+            _write_back(haystack, h)
+        index = IndexFlat(h.shape[1], metric, device=device)
+        index.train(h)
+        index.add(h)
+    else:
+        index = haystack
+    import torch
+
+    torch.cuda.synchronize(device)
+    start = time.time()
+    scores, result = index.search(q, hits)
+    scores, result = scores.cpu().numpy(), result.cpu().numpy()
+    search_time = time.time() - start
+    return result, scores, search_time
+
+
+def _write_back(host: np.ndarray, dev) -> None:
+    """faiss.normalize_L2 mutates the caller's float32 C-contiguous array; anything else it refuses."""
+    if host.dtype != np.float32 or not host.flags.c_contiguous:
+        raise TypeError("normalize_L2 expects a C-contiguous float32 array (it normalises in place)")
+    host[...] = dev.cpu().numpy()
+
+
+def proteins_search(full_sequences_data: Path, index_mode: str = "flat", k: int = 1000, device: int | None = None):
+    """pfam/proteins_search.py:11-57, flat branch: `full_sequences.npy` -> `full_sequences_flat.index`,
+    `full_sequences_flat_scores.npy`, `full_sequences_flat_hits.npy` in the same directory."""
+    if index_mode != "flat":
+        raise ValueError(index_mode + ": only the exact flat index is part of this engine")
+    device = _default_device() if device is None else device
+    full_sequences_data = Path(full_sequences_data)
+    npy = full_sequences_data.joinpath("full_sequences.npy")
+    embeddings = np.load(npy).astype(np.float32)
+    print("full_sequences", embeddings.shape)
+    start = time.time()
+    x = _upload(embeddings, device)
+    normalize_L2(x)
+    index = IndexFlat(x.shape[1], METRIC_INNER_PRODUCT, device=device)
+    index.train(x)
+    index.add(x)
+    print(f"Index creation took {int(time.time() - start)}s")
+    index_file = full_sequences_data.joinpath(f"full_sequences_{index_mode}.index")
+    write_index(index, str(index_file))
+    start = time.time()
+    flat_scores, flat_hits = index.search(x, k)
+    flat_scores, flat_hits = flat_scores.cpu().numpy(), flat_hits.cpu().numpy()
+    print(f"Search took {int(time.time() - start)}s")
+    np.save(full_sequences_data.joinpath(f"full_sequences_{index_mode}_scores.npy"), flat_scores)
+    np.save(full_sequences_data.joinpath(f"full_sequences_{index_mode}_hits.npy"), flat_hits)
+    return flat_scores, flat_hits

@@ -120,3 +120,91 @@ def test_faiss_search_flow_mutates_inputs_like_the_reference(golden_dir):
     scores, result = index.search(queries, 13)
     D_ref, I_ref = fo.knn_flat(queries, haystack, 13, 0)
     check_parity(scores, result, D_ref, I_ref, queries, haystack, 0)
+
+
+# ---- knn_b200.drivers: the same driver functions with one upload instead of three round trips -------------
+@pytest.mark.gpu
+def test_drivers_search_equals_stepwise_flow_and_golden(golden_dir, expected):
+    """knn_b200.drivers.search == cath.search.search run step by step through the alias (bit-identical), and
+    matches the (D, I) the UNMODIFIED reference driver returned over the oracle (golden)."""
+    import faiss
+
+    from knn_b200 import drivers
+
+    emb = np.load(golden_dir / "pfam-20-10/train.npy")
+    for mname, metric in [("ip", faiss.METRIC_INNER_PRODUCT), ("l2", faiss.METRIC_L2)]:
+        before = emb.copy()
+        I, D = drivers.search(emb, hits=10, metric=metric)
+        assert np.array_equal(emb, before)  # the reference normalises a copy
+        assert I.shape == (200, 10) and not I.flags.c_contiguous  # views, like results[:, 1:]
+        e = emb.copy()
+        if metric == faiss.METRIC_INNER_PRODUCT:
+            faiss.normalize_L2(e)
+        index = faiss.IndexFlat(e.shape[1], metric)
+        index.add(e)
+        s, r = index.search(e, 11)
+        assert np.array_equal(I, r[:, 1:]) and np.array_equal(D, s[:, 1:])
+        check_parity(np.ascontiguousarray(D), np.ascontiguousarray(I), expected[f"cath-search.pfam-20-10-train.{mname}.hits10.D"],
+                     expected[f"cath-search.pfam-20-10-train.{mname}.hits10.I"], e, e, metric)
+
+
+@pytest.mark.gpu
+def test_drivers_faiss_search_reference_known_answers(golden_dir, expected):
+    """tests/test_main.py:10-27 of the reference through knn_b200.drivers.faiss_search + knn_b200.evaluate_faiss."""
+    import knn_b200
+    from knn_b200 import drivers
+    from oracle.evaluate import Fixture
+
+    fx = Fixture(golden_dir / "small-random")
+    queries, haystack = np.load(fx.test), np.load(fx.train)
+    q0 = queries.copy()
+    results, scores, seconds = drivers.faiss_search(haystack, queries, 5)
+    assert seconds >= 0 and not np.array_equal(q0, queries)  # normalised in place (main.py:31)
+    np.testing.assert_allclose(np.linalg.norm(haystack, axis=1), 1.0, atol=1e-5)  # main.py:34
+    assert np.array_equal(results, expected["small-random.ip.k5.I"])
+    auc1s, tps = knn_b200.evaluate_faiss(fx, results)
+    assert auc1s == [1.0, 1 / 3, 2 / 3, 0.0, 0.0, 1 / 3] and tps == [1.0, 2 / 3, 2 / 3, 1.0, 1.0, 1.0]
+    fx = Fixture(golden_dir / "pfam-20-10")
+    results, scores, _ = drivers.faiss_search(np.load(fx.train), np.load(fx.test), 10)
+    auc1s, tps = knn_b200.evaluate_faiss(fx, results)
+    assert np.mean(auc1s) == 0.871 and np.mean(tps) == 0.91
+    # a ready index as haystack (main.py:40-41)
+    index = knn_b200.IndexFlat(1024, 0)
+    hay = np.load(fx.train)
+    knn_b200.normalize_L2(hay)
+    index.add(hay)
+    r2, s2, _ = drivers.faiss_search(index, np.load(fx.test), 10)
+    assert np.array_equal(r2, results) and np.array_equal(s2, scores)
+
+
+@pytest.mark.gpu
+def test_drivers_search_and_save_and_proteins_search(tmp_path):
+    from knn_b200 import drivers, read_index
+
+    rng = np.random.default_rng(4)
+    (tmp_path / "cath").mkdir()
+    mats = {"aac": rng.random((300, 20)).astype(np.float32), "t5_half": rng.standard_normal((200, 1024)).astype(np.float16)}
+    for name, m in mats.items():
+        np.save(tmp_path / "cath" / f"{name}.npy", m)
+    drivers.search_and_save(tmp_path / "cath")
+    for metric_name, metric in [("cosine", 0), ("euclidean", 1)]:
+        hits = np.load(tmp_path / "cath" / f"hits_{metric_name}.npz")
+        scores = np.load(tmp_path / "cath" / f"scores_{metric_name}.npz")
+        for name, m in mats.items():
+            I, D = drivers.search(m.astype(np.float32), metric=metric)
+            assert np.array_equal(hits[name], I) and np.array_equal(scores[name], D)
+            assert float((tmp_path / "cath" / f"{name}.{metric_name}-search-time.txt").read_text()) >= 0
+    emb = rng.standard_normal((3000, 1024)).astype(np.float32)
+    (tmp_path / "pfam").mkdir()
+    np.save(tmp_path / "pfam" / "full_sequences.npy", emb.astype(np.float16))
+    scores, hits = drivers.proteins_search(tmp_path / "pfam", "flat", k=1000)
+    assert np.array_equal(np.load(tmp_path / "pfam" / "full_sequences_flat_hits.npy"), hits)
+    assert np.array_equal(hits[:, 0], np.arange(3000)) and hits.shape == (3000, 1000)
+    x = emb.astype(np.float16).astype(np.float32)
+    fo.normalize_L2(x)
+    D_ref, I_ref = fo.knn_flat(x[:50], x, 1000, 0)
+    check_parity(scores[:50], hits[:50], D_ref, I_ref, x[:50], x, 0, max_excused_frac=5e-3)
+    again = read_index(str(tmp_path / "pfam" / "full_sequences_flat.index"))
+    assert again.ntotal == 3000
+    with pytest.raises(ValueError):
+        drivers.proteins_search(tmp_path / "pfam", "hnsw")
