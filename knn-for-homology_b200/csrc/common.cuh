@@ -127,6 +127,7 @@ struct FilterState {        // per query-batch, device resident
     float* cand_scores;     // [nq_pad * cap]
     uint32_t* cand_ids;     // [nq_pad * cap]
     int cap;
+    int* ovf;               // [nq] sticky per-query flag: the list ran past its capacity at some panel
 };
 struct GemmPlan;            // opaque: tensor maps + launch geometry
 int gemm_plan_create(GemmPlan** out, int device);
@@ -154,5 +155,9 @@ int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* l
 int launch_kth_lower(FilterState st, const float* eps, int64_t nq, int j, float* lower_j, cudaStream_t s);
 int launch_apply_lower(float* thr, const float* eps, const float* lower, int64_t nq, cudaStream_t s);
 int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
+// Overflow repair: out[i] = xq[idx[i]] (rows of d floats); D[idx[i]] = Dt[i], I[idx[i]] = It[i] (rows of k).
+int launch_gather_rows(const float* xq, int d, const int* idx, int64_t n, float* out, cudaStream_t s);
+int launch_scatter_results(const float* Dt, const int64_t* It, const int* idx, int64_t n, int k, float* D, int64_t* I,
+                           cudaStream_t s);
 
 }  // namespace knn

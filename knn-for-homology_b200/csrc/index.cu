@@ -91,6 +91,7 @@ struct knn_index {
     GemmPlan* plan = nullptr;
     // workspaces: exact path / staging
     DevBuf stage, xq_f32, xnorm2, eps, scores, lists_s, lists_i, overflow;
+    DevBuf ovf_q, ovf_idx, ovf_x, ovf_D, ovf_I;  // per-query overflow flags of a call and the repair staging
     DevBuf h_xq, h_D, h_I;
     // tensor path: per-query state of the filter (queries, thresholds, candidate lists)
     struct TensorWs {
@@ -113,9 +114,10 @@ struct knn_index {
     int debug_skip_epilogue = 0;
     int gemm_stages = 0;
     int panel_ratio = 0;  // 0: automatic
+    int64_t small_batch_nq = 256;  // batches up to this size use growth ratio 8
     // statistics of the last search
     int last_path = 0;
-    long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_rerank_pairs = 0;
+    long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_overflow_queries = 0, st_rerank_pairs = 0;
     double st_gemm_ms = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -234,8 +236,9 @@ int tensor_ws_ensure(knn_index::TensorWs& W, int64_t rows, int dp, int cap) {
     return KNN_OK;
 }
 
-FilterState filter_state(knn_index::TensorWs& W, int64_t off, int cap) {
+FilterState filter_state(knn_index::TensorWs& W, int64_t off, int cap, int* ovf = nullptr) {
     FilterState st;
+    st.ovf = ovf;
     st.thr = W.thr.as<float>() + off;
     st.counts = W.counts.as<int>() + off;
     st.cand_scores = W.cand_s.as<float>() + off * cap;
@@ -257,7 +260,7 @@ int tensor_prepare(knn_index* ix) {
 // growing size, survivors appended to the candidate lists, thresholds tightened after every panel.
 // On return thr[q] = (k-th best approximate score) - 2 eps[q].
 int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int64_t nb, const float* xq_batch, int k,
-                        int cap, int* d_overflow, cudaStream_t s) {
+                        int cap, int* d_overflow, int* d_ovf_q, cudaStream_t s) {
     const int64_t N = ix->ntotal;
     const int64_t nb_pad = round_up(nb, 256);
     // first panel: stored densely (every score), sized so that the list it leaves fits the register-resident
@@ -265,8 +268,11 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     int64_t first_panel = std::max<int64_t>(1024, round_up(4 * int64_t(k), 256));
     if (first_panel > cap / 2) first_panel = cap / 2;
     if (first_panel > N) first_panel = N;
-    const int ratio = ix->panel_ratio >= 2 ? ix->panel_ratio : 2;
-    FilterState st = filter_state(W, off, cap);
+    // small batches are launch-bound, not list-bound: fewer, faster growing panels (7 k' survivors per panel and query)
+    // (only while the ~7 k' survivors of the second panel fit next to the dense first panel: k' ~ 1.7 k)
+    const bool fast_growth = nb <= ix->small_batch_nq && 12 * int64_t(k) + first_panel <= cap;
+    const int ratio = ix->panel_ratio >= 2 ? ix->panel_ratio : (fast_growth ? 8 : 2);
+    FilterState st = filter_state(W, off, cap, d_ovf_q);
     float* xq_f32 = W.xq_f32.as<float>() + off * ix->dp;
     __nv_bfloat16* xq_bf16 = W.xq_bf16.as<__nv_bfloat16>() + off * ix->dp;
     KNN_CHECK(launch_prep_queries(xq_batch, nb, nb_pad, ix->d, ix->dp, xq_f32, xq_bf16, W.xnorm2.as<float>() + off,
@@ -278,7 +284,7 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
         // rows seen after each panel: P, 4P, 8P, 16P, ... (P = first, densely stored panel).  A panel runs with the
         // threshold of its start, so it appends about (r - 1) k' survivors per query (r = growth ratio, k' = rows
         // within 2 eps of the k-th): doubling keeps that at k' per panel (measured: r = 4, 8, 16 are slower).
-        const int64_t len = panel == 0 ? first_panel : (panel == 1 && ix->panel_ratio < 2 ? 3 * j0 : (ratio - 1) * j0);
+        const int64_t len = panel == 0 ? first_panel : (panel == 1 && ratio == 2 && ix->panel_ratio < 2 ? 3 * j0 : (ratio - 1) * j0);
         const int64_t j1 = j0 + len < N ? j0 + len : N;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ix->profile) {
@@ -313,17 +319,37 @@ int tensor_finish_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
 
 int redo_overflowed(knn_index* ix, int64_t nq, int64_t qb, int64_t nbatches, const float* xq_dev, int k, float* D,
                     int64_t* I, int64_t id_base, cudaStream_t s) {
-    // a candidate list that ran past its capacity (heavily duplicated / clustered scores) is never
-    // truncated silently: that batch is redone with the exact scan.
+    // A candidate list that ran past its capacity (heavily duplicated / clustered scores) is never truncated
+    // silently: exactly the queries it happened to are redone with the exact scan and their rows replaced.
     std::vector<int> h_overflow(size_t(nbatches), 0);
     KNN_CHECK_CUDA(cudaMemcpyAsync(h_overflow.data(), ix->overflow.p, sizeof(int) * size_t(nbatches), cudaMemcpyDeviceToHost, s));
     KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    std::vector<int> redo;
+    std::vector<int> flags;
     for (int64_t b = 0; b < nbatches; ++b) {
         if (!h_overflow[size_t(b)]) continue;
         const int64_t q0 = b * qb;
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
         ix->st_overflow_batches++;
-        KNN_CHECK(search_exact(ix, nb, xq_dev + q0 * ix->d, k, D + q0 * k, I + q0 * k, id_base, s));
+        flags.resize(size_t(nb));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(flags.data(), ix->ovf_q.as<int>() + q0, sizeof(int) * size_t(nb), cudaMemcpyDeviceToHost, s));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        for (int64_t i = 0; i < nb; ++i)
+            if (flags[size_t(i)]) redo.push_back(int(q0 + i));
+    }
+    ix->st_overflow_queries += (long long)redo.size();
+    const int64_t chunk = 1024;
+    for (size_t c0 = 0; c0 < redo.size(); c0 += size_t(chunk)) {
+        const int64_t n = int64_t(std::min(redo.size() - c0, size_t(chunk)));
+        KNN_CHECK(ix->ovf_idx.ensure(sizeof(int) * size_t(chunk)));
+        KNN_CHECK(ix->ovf_x.ensure(sizeof(float) * size_t(chunk) * ix->d));
+        KNN_CHECK(ix->ovf_D.ensure(sizeof(float) * size_t(chunk) * k));
+        KNN_CHECK(ix->ovf_I.ensure(sizeof(int64_t) * size_t(chunk) * k));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(ix->ovf_idx.p, redo.data() + c0, sizeof(int) * size_t(n), cudaMemcpyHostToDevice, s));
+        KNN_CHECK(launch_gather_rows(xq_dev, ix->d, ix->ovf_idx.as<int>(), n, ix->ovf_x.as<float>(), s));
+        KNN_CHECK(search_exact(ix, n, ix->ovf_x.as<float>(), k, ix->ovf_D.as<float>(), ix->ovf_I.as<int64_t>(), id_base, s));
+        KNN_CHECK(launch_scatter_results(ix->ovf_D.as<float>(), ix->ovf_I.as<int64_t>(), ix->ovf_idx.as<int>(), n, k, D, I, s));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));  // `redo` chunk consumed
     }
     return KNN_OK;
 }
@@ -337,12 +363,14 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     const int64_t nbatches = (nq + qb - 1) / qb;
     KNN_CHECK(tensor_ws_ensure(ix->ws1, qb, ix->dp, cap));
     KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(nbatches)));
+    KNN_CHECK(ix->ovf_q.ensure(sizeof(int) * size_t(nq)));
     KNN_CHECK(tensor_prepare(ix));
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(nbatches), s));
     for (int64_t b = 0; b < nbatches; ++b) {
         const int64_t q0 = b * qb;
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
-        KNN_CHECK(tensor_filter_batch(ix, ix->ws1, 0, nb, xq_dev + q0 * ix->d, k, cap, ix->overflow.as<int>() + b, s));
+        KNN_CHECK(tensor_filter_batch(ix, ix->ws1, 0, nb, xq_dev + q0 * ix->d, k, cap, ix->overflow.as<int>() + b,
+                                      ix->ovf_q.as<int>() + q0, s));
         KNN_CHECK(tensor_finish_batch(ix, ix->ws1, 0, nb, k, cap, nullptr, D + q0 * k, I + q0 * k, id_base, s));
     }
     return redo_overflowed(ix, nq, qb, nbatches, xq_dev, k, D, I, id_base, s);
@@ -371,6 +399,7 @@ int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64,
     ix->st_gemm_launches = 0;
     ix->st_gemm_ms = 0;
     ix->st_overflow_batches = 0;
+    ix->st_overflow_queries = 0;
     ix->ev_used = 0;
     int rc;
     if (ix->ntotal == 0) {
@@ -496,7 +525,7 @@ int knn_index_free(knn_index* ix) {
     DeviceGuard g(ix->device);
     cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xnorm2, &ix->eps, &ix->scores, &ix->lists_s, &ix->lists_i,
-                      &ix->overflow, &ix->h_xq, &ix->h_D, &ix->h_I})
+                      &ix->overflow, &ix->ovf_q, &ix->ovf_idx, &ix->ovf_x, &ix->ovf_D, &ix->ovf_I, &ix->h_xq, &ix->h_D, &ix->h_I})
         b->release();
     for (knn_index::TensorWs* W : {&ix->ws1, &ix->ws2})
         for (DevBuf* b : {&W->xq_f32, &W->xq_bf16, &W->xnorm2, &W->eps, &W->thr, &W->counts, &W->cand_s, &W->cand_i}) b->release();
@@ -595,7 +624,7 @@ int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, floa
     KNN_CHECK(ix->h_xq.ensure(size_t(nb_max) * ix->d * sizeof(float)));
     KNN_CHECK(ix->h_D.ensure(size_t(nb_max) * k * sizeof(float)));
     KNN_CHECK(ix->h_I.ensure(size_t(nb_max) * k * sizeof(int64_t)));
-    long long launches = 0, gemm_launches = 0, overflow = 0;
+    long long launches = 0, gemm_launches = 0, overflow = 0, overflow_q = 0;
     double gemm_ms = 0;
     for (int64_t q0 = 0; q0 < nq; q0 += hb) {
         const int64_t nb = nq - q0 < hb ? nq - q0 : hb;
@@ -608,11 +637,13 @@ int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, floa
         gemm_launches += ix->st_gemm_launches;
         gemm_ms += ix->st_gemm_ms;
         overflow += ix->st_overflow_batches;
+        overflow_q += ix->st_overflow_queries;
     }
     ix->st_launches = launches;
     ix->st_gemm_launches = gemm_launches;
     ix->st_gemm_ms = gemm_ms;
     ix->st_overflow_batches = overflow;
+    ix->st_overflow_queries = overflow_q;
     return KNN_OK;
 }
 
@@ -637,6 +668,7 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     ix->st_gemm_launches = 0;
     ix->st_gemm_ms = 0;
     ix->st_overflow_batches = 0;
+    ix->st_overflow_queries = 0;
     ix->ev_used = 0;
     auto& P = ix->pend;
     P = knn_index::Pending();
@@ -655,12 +687,14 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     P.nbatches = (nq + P.qb - 1) / P.qb;
     KNN_CHECK(tensor_ws_ensure(ix->ws2, P.nbatches * P.qb, ix->dp, P.cap));
     KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(P.nbatches)));
+    KNN_CHECK(ix->ovf_q.ensure(sizeof(int) * size_t(nq)));
     KNN_CHECK(tensor_prepare(ix));
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(P.nbatches), s));
     for (int64_t b = 0; b < P.nbatches; ++b) {
         const int64_t q0 = b * P.qb;
         const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
-        KNN_CHECK(tensor_filter_batch(ix, ix->ws2, q0, nb, xq_dev + q0 * ix->d, k, P.cap, ix->overflow.as<int>() + b, s));
+        KNN_CHECK(tensor_filter_batch(ix, ix->ws2, q0, nb, xq_dev + q0 * ix->d, k, P.cap, ix->overflow.as<int>() + b,
+                                      ix->ovf_q.as<int>() + q0, s));
     }
     // lower[q] = thr + eps = (k-th best approximate score) - eps: a lower bound of the true k-th best score
     KNN_CHECK(launch_export_lower(ix->ws2.thr.as<float>(), ix->ws2.eps.as<float>(), nq, lower_dev, s));
@@ -763,6 +797,7 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "l2_hints") ix->l2_hints = value != 0;
     else if (n == "gemm_stages" && value >= 0 && value <= 6) ix->gemm_stages = int(value);
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
+    else if (n == "small_batch_nq" && value >= 0) ix->small_batch_nq = value;
     else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
@@ -781,6 +816,7 @@ int knn_index_get_stat(const knn_index* ix, const char* name, double* out) {
     else if (n == "gemm_launches") *out = double(ix->st_gemm_launches);
     else if (n == "gemm_ms") *out = ix->st_gemm_ms;
     else if (n == "overflow_batches") *out = double(ix->st_overflow_batches);
+    else if (n == "overflow_queries") *out = double(ix->st_overflow_queries);
     else if (n == "capacity") *out = double(ix->capacity);
     else {
         set_error("get_stat: unknown statistic %s", name);

@@ -259,13 +259,16 @@ struct TightenSmem {
 __global__ void __launch_bounds__(256)
 tighten_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __restrict__ cand_scores,
                uint32_t* __restrict__ cand_ids, int cap, const float* __restrict__ eps, int k, int compact,
-               int* __restrict__ overflow) {
+               int* __restrict__ overflow, int* __restrict__ ovf_q) {
     __shared__ TightenSmem sm;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x;
     int cnt = counts[q];
     if (cnt > cap) {
-        if (tid == 0) atomicExch(overflow, 1);
+        if (tid == 0) {
+            atomicExch(overflow, 1);
+            ovf_q[q] = 1;
+        }
         cnt = cap;
     }
     if (cnt < k || cnt == 0) return;  // fewer than k candidates seen: everything stays a candidate
@@ -403,7 +406,7 @@ __device__ __forceinline__ uint32_t warp_kth_largest_mem(const float* __restrict
 __global__ void __launch_bounds__(256)
 tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __restrict__ cand_scores,
                     uint32_t* __restrict__ cand_ids, int cap, const float* __restrict__ eps, int64_t nq, int k,
-                    int* __restrict__ overflow) {
+                    int* __restrict__ overflow, int* __restrict__ ovf_q) {
     const int lane = threadIdx.x & 31;
     const int64_t q = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -411,7 +414,10 @@ tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __
     const float two_eps = 2.0f * eps[q];
     const float old = thr[q];
     if (cnt > cap) {
-        if (lane == 0) atomicExch(overflow, 1);
+        if (lane == 0) {
+            atomicExch(overflow, 1);
+            ovf_q[q] = 1;
+        }
         cnt = cap;
     }
     if (cnt < k || cnt == 0) return;  // fewer than k candidates seen: everything stays a candidate
@@ -548,11 +554,27 @@ __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
     if (i < n) p[i] = v;
 }
 
-__global__ void init_filter_kernel(float* thr, int* counts, int64_t nq, int64_t nq_pad, int first_count) {
+__global__ void init_filter_kernel(float* thr, int* counts, int* ovf, int64_t nq, int64_t nq_pad, int first_count) {
     const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q >= nq_pad) return;
     thr[q] = q < nq ? -FLT_MAX : FLT_MAX;
     counts[q] = q < nq ? first_count : 0;
+    if (q < nq) ovf[q] = 0;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ xq, int d, const int* __restrict__ idx, float* __restrict__ out) {
+    const float* src = xq + int64_t(idx[blockIdx.x]) * d;
+    float* dst = out + int64_t(blockIdx.x) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void scatter_results_kernel(const float* __restrict__ Dt, const int64_t* __restrict__ It, const int* __restrict__ idx,
+                                       int k, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int64_t q = idx[blockIdx.x];
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+        D[q * k + r] = Dt[int64_t(blockIdx.x) * k + r];
+        I[q * k + r] = It[int64_t(blockIdx.x) * k + r];
+    }
 }
 
 }  // namespace
@@ -603,10 +625,10 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
     if (nq <= 0) return KNN_OK;
     if (k <= 256 && compact) {
         tighten_warp_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap,
-                                                                   eps, nq, k, overflow);
+                                                                   eps, nq, k, overflow, st.ovf);
     } else {
         tighten_kernel<<<unsigned(nq), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap, eps, k,
-                                                    compact, overflow);
+                                                    compact, overflow, st.ovf);
     }
     KNN_CHECK_LAUNCH();
     return KNN_OK;
@@ -637,7 +659,22 @@ int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s) {
 }
 
 int launch_init_filter(FilterState st, int64_t nq, int64_t nq_pad, int first_count, cudaStream_t s) {
-    init_filter_kernel<<<unsigned((nq_pad + 255) / 256), 256, 0, s>>>(st.thr, st.counts, nq, nq_pad, first_count);
+    init_filter_kernel<<<unsigned((nq_pad + 255) / 256), 256, 0, s>>>(st.thr, st.counts, st.ovf, nq, nq_pad, first_count);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_gather_rows(const float* xq, int d, const int* idx, int64_t n, float* out, cudaStream_t s) {
+    if (n <= 0) return KNN_OK;
+    gather_rows_kernel<<<unsigned(n), 256, 0, s>>>(xq, d, idx, out);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int launch_scatter_results(const float* Dt, const int64_t* It, const int* idx, int64_t n, int k, float* D, int64_t* I,
+                           cudaStream_t s) {
+    if (n <= 0) return KNN_OK;
+    scatter_results_kernel<<<unsigned(n), 256, 0, s>>>(Dt, It, idx, k, D, I);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }

@@ -261,6 +261,24 @@ def test_candidate_overflow_falls_back_not_truncates(knn):
     assert np.array_equal(I, np.tile(np.arange(k), (128, 1)))
 
 
+def test_overflow_repairs_only_the_queries_it_happened_to(knn):
+    """A few queries sit in a huge clump of identical rows (their lists overflow), the rest of the batch is ordinary:
+    only the clump queries are redone by the exact scan, and every row of the result still equals the exact path."""
+    rng = np.random.default_rng(8)
+    nb, d, k = 60000, 128, 20
+    xb = rng.standard_normal((nb, d)).astype(np.float32)
+    clump = rng.standard_normal(d).astype(np.float32)
+    xb[10000:40000] = clump  # 30,000 identical rows > candidate capacity (8192)
+    xq = rng.standard_normal((500, d)).astype(np.float32)
+    xq[[3, 77, 400]] = clump
+    D, I, idx = _search(knn, xq, xb, k, IP, path=2)
+    # the 3 clump queries, plus the few whose early (looser) panel threshold still let the clump in
+    assert idx.stat("overflow_batches") == 1 and 3 <= idx.stat("overflow_queries") < 100
+    D1, I1, _ = _search(knn, xq, xb, k, IP, path=1)
+    assert np.array_equal(I, I1) and np.array_equal(D, D1)
+    assert np.array_equal(I[3], np.arange(10000, 10000 + k))  # ties: lower id first
+
+
 def test_incremental_add_and_reset(knn):
     xq, xb = _data(40, 6000, 256, seed=3)
     idx = knn.IndexFlat(256, IP)
