@@ -1,6 +1,7 @@
 // Shared declarations for libknn_b200.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cfloat>
@@ -83,17 +84,26 @@ __host__ __device__ inline uint32_t key_id(uint64_t key) { return ~uint32_t(key)
 // ---- kernel launchers (one translation unit each) ---------------------------------------
 struct DbStats {          // device-resident, updated by the ingest kernel with atomicMax on
     unsigned max_norm2;   // float bits (values are >= 0, so the uint order is the float order)
-    unsigned max_dnorm2;  // max |y - bf16(y)|^2
+    unsigned max_dnorm2;  // max |y - shadow(y)|^2
 };
+
+// 16-bit format of the tensor-core operands (the "shadow" copies of database rows and queries).  Both feed
+// tcgen05.mma kind::f16 at the same rate; fp16 carries 3 more mantissa bits, i.e. an 8 x smaller rounding term
+// in the error bound, but a narrow exponent range - out-of-range values saturate / flush to zero at conversion
+// and show up in the MEASURED |y - shadow(y)|, so the bound stays rigorous for either format.
+enum ShadowFmt : int { kFmtBF16 = 0, kFmtFP16 = 1 };
+typedef uint16_t h16_t;   // raw 16-bit storage of a shadow element
 
 // kernels_basic.cu
 int launch_normalize_l2(float* x, int64_t n, int64_t d, cudaStream_t s);
-int launch_ingest(const float* src, int64_t n, int d, int dp, float* dst_f32, __nv_bfloat16* dst_bf16,
-                  float* norms2, DbStats* stats, cudaStream_t s);
-// Queries -> zero-padded fp32 (ld = dp) and bf16 copies, |x|^2 and the score error bound eps
-// (see DESIGN.md "error bound"); rows [nq, nq_pad) of the bf16 copy are zeroed.
+// src rows of d floats (stride src_ld) -> zero-padded fp32 master rows (optional), 16-bit shadow rows in format
+// `fmt`, |y|^2 (optional) and the running maxima in *stats.  shadow_is_master: the rounded values ARE the row.
+int launch_ingest(const float* src, int64_t src_ld, int64_t n, int d, int dp, float* dst_f32, h16_t* dst_h16, int fmt,
+                  bool shadow_is_master, float* norms2, DbStats* stats, cudaStream_t s);
+// Queries -> zero-padded fp32 (ld = dp) and 16-bit copies, |x|^2 and the score error bound eps
+// (see DESIGN.md "error bound"); rows [nq, nq_pad) of the 16-bit copy are zeroed.
 int launch_prep_queries(const float* xq, int64_t nq, int64_t nq_pad, int d, int dp, float* xq_f32,
-                        __nv_bfloat16* xq_bf16, float* xnorm2, float* eps, const DbStats* stats,
+                        h16_t* xq_h16, int fmt, float* xnorm2, float* eps, const DbStats* stats,
                         int metric, cudaStream_t s);
 // Exact fp32 scores of queries [0, nqt) (nqt <= kScanMaxQueries... looped inside) against rows
 // [j0, j1): out[q * ld_out + (j - j0)] = <x_q, y_j> (IP) or max(0, |x|^2 + |y|^2 - 2<x,y>) (L2).
@@ -137,11 +147,11 @@ void gemm_plan_set_l2_hints(GemmPlan* p, int on);
 void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue);
 void gemm_plan_set_stages(GemmPlan* p, int stages);
 int gemm_plan_query_rows_multiple(const GemmPlan* p);     // nq_pad granularity of the chosen variant
-// Scores queries (bf16, [nq_pad x dp]) against database rows [j0, j1) (bf16, [ntotal x dp]) on the
-// tensor cores and appends every (score, id) with score >= thr[q] to the candidate lists.
+// Scores queries (16-bit, format fmt_q, [nq_pad x dp]) against database rows [j0, j1) (16-bit, format fmt_db,
+// [ntotal x dp]) on the tensor cores and appends every (score, id) with score >= thr[q] to the candidate lists.
 // dense_first: rows are stored at slot (j - j0) without atomics (first panel, thr = -inf).
-int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, int64_t nq_pad, int dp,
-                       const __nv_bfloat16* xb_bf16, int64_t ntotal, const float* ynorm2, int64_t j0,
+int gemm_filter_launch(GemmPlan* p, const h16_t* xq_h16, int fmt_q, int64_t nq, int64_t nq_pad, int dp,
+                       const h16_t* xb_h16, int fmt_db, int64_t ntotal, const float* ynorm2, int64_t j0,
                        int64_t j1, int metric, bool dense_first, FilterState st, cudaStream_t s);
 // After a panel: thr[q] <- (k-th best approx score so far) - 2*eps[q]; drops candidates below the
 // new threshold; raises *overflow when a list ran past its capacity.
