@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-phases", action="store_true", help="skip the extra untimed pass that times the phases of the sharded search")
     ap.add_argument("--bf16-storage", action="store_true", help="the bf16 values ARE the database (config C5): no fp32 master rows")
+    ap.add_argument("--shadow-fmt", type=int, default=0, choices=[0, 1, 2], help="16-bit format of the tensor-core copy of the database: 0 automatic, 1 bf16, 2 fp16")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: equal row shards instead of shards proportional to each GPU's measured speed")
+    ap.add_argument("--mantissa-bits", type=int, default=0, help="mantissa bits kept in bf16 tensor-core operands: 0 automatic, 2..7")
     return ap.parse_args()
 
 
@@ -175,7 +178,7 @@ def main():
     import torch.distributed as dist
 
     import knn_b200
-    from knn_b200.distributed import ShardedIndexFlat, shard_bounds
+    from knn_b200.distributed import ShardedIndexFlat, measured_rank_speeds, shard_bounds
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -183,11 +186,21 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- build the database shard on the device (index build is reported, not timed as search) ----
+    # A step ends when the slowest shard is done, and under the board power cap the GPUs of one box do not clock
+    # alike: shards are sized in proportion to each GPU's measured speed on the engine's own GEMM (2 s, untimed, part
+    # of the index build like any placement decision).
+    weights = None
+    if world > 1 and not args.no_balance:
+        weights = measured_rank_speeds(D_DIM, local_rank, seconds=2.0)
     t_build = time.perf_counter()
-    index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank, bf16_storage=args.bf16_storage)
-    b = shard_bounds(args.nb, world)
+    index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank, bf16_storage=args.bf16_storage,
+                             shard_weights=weights)
+    b = shard_bounds(args.nb, world, weights)
     lo, hi = b[rank], b[rank + 1]
     index.local.set_param("cta_group", args.cta_group)
+    if args.shadow_fmt and not args.bf16_storage:
+        index.local.set_param("shadow_fmt", args.shadow_fmt)
+    index.local.set_param("mantissa_bits", args.mantissa_bits)
     index.local.reserve(hi - lo)
     for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
         r0, r1 = blk * BLOCK_ROWS, min((blk + 1) * BLOCK_ROWS, args.nb)
@@ -284,6 +297,9 @@ def main():
     # parity spot check inside the bench: a few queries rescored exhaustively by the exact fp32 path
     D, I = last["DI"]  # result of the last timed step
     search_path = int(index.local.stat("path"))
+    fmt_names = {1: "bf16", 2: "fp16"}
+    fmt = fmt_names[int(index.local.stat("shadow_fmt"))]
+    mbits = int(index.local.stat("mantissa_bits"))
     chk = torch.arange(0, args.nq, max(1, args.nq // 64), device=dev)[:64]
     index.local.set_param("path", 1)
     D1, I1 = index.search(xq_dev[chk].contiguous(), args.k)
@@ -303,7 +319,7 @@ def main():
         achieved = flops_per_step * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         peak = peaks["tflops_sustained"]
         traffic, traffic_note = ncu_traffic()
-        roofline = {"bound": "tensor", "kernel": "gemm_filter_kernel (tcgen05 bf16, fused threshold filter)",
+        roofline = {"bound": "tensor", "kernel": "gemm_filter_kernel (tcgen05 kind::f16, fused threshold filter)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None, "peak_kind": "sustained, " + peaks["source"],
                     "frac_of_burst": (achieved / peaks["tflops_burst"]) if achieved else None,
@@ -320,11 +336,14 @@ def main():
             "metric": "queries/s at 1024-d, k=%d, exact flat inner-product search" % args.k,
             "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "dtype_note": "bf16 x bf16 -> f32 tensor-core filter, then exact f32 rescoring: results equal f32 IndexFlatIP",
+            "dtype": fmt, "dtype_note": f"{fmt} x {fmt} ({mbits} mantissa bits) -> f32 tensor-core filter (tcgen05 kind::f16), then exact f32 "
+                                        "rescoring: results equal f32 IndexFlatIP",
             "data": "synthetic",
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
             "search_path": search_path, "cta_group": args.cta_group, "phases_ms_rank0": phases, "ms_per_step_by_rank": by_rank_value or None,
+            "shard_rows_by_rank": [b[r + 1] - b[r] for r in range(world)],
+            "rank_speed_weights": [round(w, 4) for w in weights] if weights else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -98,12 +98,13 @@ typedef uint16_t h16_t;   // raw 16-bit storage of a shadow element
 int launch_normalize_l2(float* x, int64_t n, int64_t d, cudaStream_t s);
 // src rows of d floats (stride src_ld) -> zero-padded fp32 master rows (optional), 16-bit shadow rows in format
 // `fmt`, |y|^2 (optional) and the running maxima in *stats.  shadow_is_master: the rounded values ARE the row.
+// mbits: explicit mantissa bits kept in a bf16 shadow (7 = all of them; ignored for fp16 and for master rows).
 int launch_ingest(const float* src, int64_t src_ld, int64_t n, int d, int dp, float* dst_f32, h16_t* dst_h16, int fmt,
-                  bool shadow_is_master, float* norms2, DbStats* stats, cudaStream_t s);
+                  int mbits, bool shadow_is_master, float* norms2, DbStats* stats, cudaStream_t s);
 // Queries -> zero-padded fp32 (ld = dp) and 16-bit copies, |x|^2 and the score error bound eps
 // (see DESIGN.md "error bound"); rows [nq, nq_pad) of the 16-bit copy are zeroed.
 int launch_prep_queries(const float* xq, int64_t nq, int64_t nq_pad, int d, int dp, float* xq_f32,
-                        h16_t* xq_h16, int fmt, float* xnorm2, float* eps, const DbStats* stats,
+                        h16_t* xq_h16, int fmt, int mbits, float* xnorm2, float* eps, const DbStats* stats,
                         int metric, cudaStream_t s);
 // Exact fp32 scores of queries [0, nqt) (nqt <= kScanMaxQueries... looped inside) against rows
 // [j0, j1): out[q * ld_out + (j - j0)] = <x_q, y_j> (IP) or max(0, |x|^2 + |y|^2 - 2<x,y>) (L2).

@@ -1,12 +1,12 @@
 // Distance GEMM with a fused threshold-filter epilogue for sm_100a: TMA (128-byte swizzle) ->
-// shared memory -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld -> compare against
+// shared memory -> tcgen05.mma (16-bit x 16-bit -> fp32 in TMEM; bf16 or fp16 per operand) -> tcgen05.ld -> compare against
 // the per-query candidate threshold -> rare append to the per-query candidate list.  The
 // nq x N score matrix never reaches HBM.
 //
 // This is the one dense contraction of the flat-search path: the `sgemm` inside faiss's
 // knn_inner_product / knn_L2sqr behind index.search (reference call sites cath/search.py:24,
 // pfam/proteins_search.py:49, seqvec_search/main.py:45; faiss itself is third-party, see
-// oracle/flat_oracle.py).  Scores produced here are approximate (bf16 inputs); the candidate
+// oracle/flat_oracle.py).  Scores produced here are approximate (16-bit inputs); the candidate
 // threshold carries the error bound and the survivors are rescored in fp32 (rerank_kernel).
 //
 // Tile per CTA: 128 queries (TMEM lanes) x 256 database rows (TMEM columns) x 64 (one 128-byte
@@ -52,10 +52,13 @@ struct Cfg {
         return size_t(stages) * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * (512 * 8 + 8 * 32 * 16) + 16 /*EpilogueSmem*/;
     }
     static constexpr size_t kSmemBytes = smem_bytes(kStages);
-    // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+    // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A format at bits 7-9 and B format at bits 10-12
+    // (0 = F16, 1 = BF16, chosen per launch: the operands' 16-bit formats are independent of each other),
     // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 (M = 256 for a CTA pair).
-    static constexpr uint32_t kInstrDesc =
-        (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t((BM * CG) >> 4) << 24);
+    static constexpr uint32_t kInstrDescBase = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((BM * CG) >> 4) << 24);
+    static uint32_t instr_desc(int fmt_a, int fmt_b) {
+        return kInstrDescBase | ((fmt_a == kFmtBF16 ? 1u : 0u) << 7) | ((fmt_b == kFmtBF16 ? 1u : 0u) << 10);
+    }
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -149,9 +152,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     }
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T: one (128*CG) x 256 x 16 bf16 MMA (CG = 2: across the CTA pair)
+// D[tmem] (+)= A[smem] * B[smem]^T: one (128*CG) x 256 x 16 MMA of 16-bit operands (CG = 2: across the CTA pair)
 template <int CG>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     if constexpr (CG == 1) {
         asm volatile(
             "{\n"
@@ -236,6 +239,7 @@ struct GemmArgs {
     int cap;
     uint64_t hint_q, hint_db;  // L2 eviction-priority policies of the two TMA streams
     int stages;                // shared-memory pipeline depth
+    uint32_t idesc;            // tcgen05 instruction descriptor (operand formats of this launch)
     int debug_skip_epilogue;   // experiments only: accumulators are not read (results are then meaningless)
 };
 
@@ -382,7 +386,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
-                        umma_bf16<CG>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), C::kInstrDesc, (kb | k) ? 1u : 0u);
+                        umma_f16<CG>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), args.idesc, (kb | k) ? 1u : 0u);
                     }
                     umma_commit<CG>(&bars->empty[stage]);  // smem slot reusable once these MMAs have read it
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -583,12 +587,13 @@ int gemm_plan_create(GemmPlan** out, int device) {
 
 void gemm_plan_destroy(GemmPlan* p) { delete p; }
 
-static int make_map(GemmPlan* p, CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int dp, int box_rows) {
+// The tensor map only moves 16-bit elements (zero fill out of bounds): one map type serves bf16 and fp16 rows.
+static int make_map(GemmPlan* p, CUtensorMap* map, const h16_t* base, int64_t rows, int dp, int box_rows) {
     cuuint64_t gdim[2] = {cuuint64_t(dp), cuuint64_t(rows)};
     cuuint64_t gstride[1] = {cuuint64_t(dp) * 2};
     cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = p->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstride, box, estr,
+    CUresult r = p->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<h16_t*>(base), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -601,11 +606,13 @@ static int make_map(GemmPlan* p, CUtensorMap* map, const __nv_bfloat16* base, in
 template <int CG, bool L2, bool DENSE>
 static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorMap& map_db, const GemmArgs& a, cudaStream_t s) {
     auto kern = gemm_filter_kernel<CG, L2, DENSE>;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
+    static bool attr_done[64] = {};  // per instantiation and device (function attributes are per device)
+    int dev = 0;
+    KNN_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(Cfg<CG>::smem_bytes(CG == 1 ? 4 : kMaxStages))));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;
     const int units_max = p->sms / CG;
@@ -627,8 +634,8 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     return KNN_OK;
 }
 
-int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, int64_t nq_pad, int dp,
-                       const __nv_bfloat16* xb_bf16, int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1,
+int gemm_filter_launch(GemmPlan* p, const h16_t* xq_h16, int fmt_q, int64_t nq, int64_t nq_pad, int dp,
+                       const h16_t* xb_h16, int fmt_db, int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1,
                        int metric, bool dense_first, FilterState st, cudaStream_t s) {
     if (j1 <= j0 || nq <= 0) return KNN_OK;
     const int cg = p->cta_group;
@@ -641,8 +648,8 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
         return KNN_ERR_INVALID;
     }
     CUtensorMap map_q, map_db;
-    KNN_CHECK(make_map(p, &map_q, xq_bf16, nq_pad, dp, BM));
-    KNN_CHECK(make_map(p, &map_db, xb_bf16, ntotal, dp, BN / cg));
+    KNN_CHECK(make_map(p, &map_q, xq_h16, nq_pad, dp, BM));
+    KNN_CHECK(make_map(p, &map_db, xb_h16, ntotal, dp, BN / cg));
     GemmArgs a;
     a.nq = nq;
     a.m_tiles = int(nq_pad / (BM * cg));
@@ -657,6 +664,7 @@ int gemm_filter_launch(GemmPlan* p, const __nv_bfloat16* xq_bf16, int64_t nq, in
     a.cand_ids = st.cand_ids;
     a.cap = st.cap;
     a.debug_skip_epilogue = p->debug_skip_epilogue;
+    a.idesc = cg == 1 ? Cfg<1>::instr_desc(fmt_q, fmt_db) : Cfg<2>::instr_desc(fmt_q, fmt_db);
     a.stages = cg == 1 ? Cfg<1>::kStages : Cfg<2>::kStages;
     if (p->stages >= 2 && p->stages <= (cg == 1 ? 4 : kMaxStages)) a.stages = p->stages;
     a.hint_q = p->l2_hints ? kEvictLast : kEvictNormal;

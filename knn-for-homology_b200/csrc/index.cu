@@ -7,7 +7,7 @@
 //
 // Two device paths, both CUDA only:
 //   exact  : fp32 scan kernel -> dense scores -> two-level radix select          (small nq / small N)
-//   tensor : tcgen05 bf16 GEMM with threshold-filter epilogue over growing database panels,
+//   tensor : tcgen05 GEMM over 16-bit shadow copies (fp16 or bf16) with threshold-filter epilogue over growing database panels,
 //            per-panel threshold tightening, exact fp32 rerank of the surviving candidates,
 //            final radix select                                                   (large batches)
 // The tensor path returns exactly what the exact path returns: the filter keeps a provable
@@ -83,7 +83,11 @@ struct knn_index {
     unsigned flags = 0;
     int64_t ntotal = 0, capacity = 0;
     float* xb_f32 = nullptr;          // [capacity x dp] zero-padded rows (absent with BF16_STORAGE)
-    __nv_bfloat16* xb_bf16 = nullptr; // [capacity x dp]
+    h16_t* xb_h16 = nullptr;          // [capacity x dp] 16-bit shadow rows, format shadow_fmt (bf16 with BF16_STORAGE: the rows themselves)
+    int shadow_fmt = kFmtBF16;        // format of ALL shadow rows (see desired_shadow / prepare_shadow)
+    int shadow_mbits = 7;             // explicit mantissa bits kept in bf16 shadow rows
+    bool stats_dirty = false;         // rows were added since the shadow's rounding error was last looked at
+    bool fp16_unfit = false;          // the data leaves fp16's exponent range (measured): automatic choice stays bf16
     float* ynorm2 = nullptr;          // [capacity]
     DbStats* stats = nullptr;
     cudaStream_t stream = nullptr;
@@ -95,7 +99,7 @@ struct knn_index {
     DevBuf h_xq, h_D, h_I;
     // tensor path: per-query state of the filter (queries, thresholds, candidate lists)
     struct TensorWs {
-        DevBuf xq_f32, xq_bf16, xnorm2, eps, thr, counts, cand_s, cand_i;
+        DevBuf xq_f32, xq_h16, xnorm2, eps, thr, counts, cand_s, cand_i;
     };
     TensorWs ws1;  // one query batch (single-call search)
     TensorWs ws2;  // all queries of a two-phase search (filter ... exchange ... finish)
@@ -115,9 +119,11 @@ struct knn_index {
     int gemm_stages = 0;
     int panel_ratio = 0;  // 0: automatic
     int64_t small_batch_nq = 256;  // batches up to this size use growth ratio 8
+    int shadow_param = 0;          // 16-bit format of the tensor-core operands: 0 automatic (desired_shadow), 1 bf16, 2 fp16
+    int mbits_param = 0;           // mantissa bits kept in bf16 operands: 0 automatic, 2..7
     // statistics of the last search
     int last_path = 0;
-    long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_overflow_queries = 0, st_rerank_pairs = 0;
+    long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_overflow_queries = 0, st_rerank_pairs = 0, st_shadow_conversions = 0;
     double st_gemm_ms = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -139,11 +145,11 @@ int grow(knn_index* ix, int64_t want_rows, bool exact = false) {
     // rows may have been ingested on a caller's stream: settle everything before moving them
     KNN_CHECK_CUDA(cudaDeviceSynchronize());
     float* nf = nullptr;
-    __nv_bfloat16* nb = nullptr;
+    h16_t* nb = nullptr;
     float* nn = nullptr;
     cudaError_t e = cudaSuccess;
     if (!bf16_only(ix)) e = cudaMalloc(&nf, size_t(cap) * ix->dp * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&nb, size_t(cap) * ix->dp * sizeof(__nv_bfloat16));
+    if (e == cudaSuccess) e = cudaMalloc(&nb, size_t(cap) * ix->dp * sizeof(h16_t));
     if (e == cudaSuccess) e = cudaMalloc(&nn, size_t(cap) * sizeof(float));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -156,15 +162,15 @@ int grow(knn_index* ix, int64_t want_rows, bool exact = false) {
     }
     if (ix->ntotal > 0) {
         if (nf) KNN_CHECK_CUDA(cudaMemcpyAsync(nf, ix->xb_f32, size_t(ix->ntotal) * ix->dp * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
-        KNN_CHECK_CUDA(cudaMemcpyAsync(nb, ix->xb_bf16, size_t(ix->ntotal) * ix->dp * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, ix->stream));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(nb, ix->xb_h16, size_t(ix->ntotal) * ix->dp * sizeof(h16_t), cudaMemcpyDeviceToDevice, ix->stream));
         KNN_CHECK_CUDA(cudaMemcpyAsync(nn, ix->ynorm2, size_t(ix->ntotal) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
         KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
     }
     if (ix->xb_f32) cudaFree(ix->xb_f32);
-    if (ix->xb_bf16) cudaFree(ix->xb_bf16);
+    if (ix->xb_h16) cudaFree(ix->xb_h16);
     if (ix->ynorm2) cudaFree(ix->ynorm2);
     ix->xb_f32 = nf;
-    ix->xb_bf16 = nb;
+    ix->xb_h16 = nb;
     ix->ynorm2 = nn;
     ix->capacity = cap;
     return KNN_OK;
@@ -177,6 +183,76 @@ cudaEvent_t next_event(knn_index* ix) {
         ix->ev_pool.push_back(e);
     }
     return ix->ev_pool[ix->ev_used++];
+}
+
+// ---- 16-bit shadow format -------------------------------------------------------------------
+const __nv_bfloat16* bf16_rows(const knn_index* ix) { return reinterpret_cast<const __nv_bfloat16*>(ix->xb_h16); }
+
+constexpr int kAutoMantissaBits = 7;
+
+struct ShadowChoice {
+    int fmt, mbits;
+};
+
+// Which 16-bit format serves a search of the k best among n rows (k = 0: not known yet, at add time).
+// Both formats run tcgen05.mma kind::f16 at the same rate per clock; they differ in two measured ways
+// (profiles/r01_shadow_formats.md): fp16's 3 extra mantissa bits shrink the rounding term of the error bound 8 x,
+// i.e. fewer candidates to rescore exactly - and they cost multiplier power, which under the board's power cap is
+// ~6 % of the clock in a long GEMM.  So fp16 where the rescoring dominates (k large against n), bf16 where the
+// GEMM does.  The shadow is rewritten from the fp32 master rows when the regime changes (one pass over the rows).
+ShadowChoice desired_shadow(const knn_index* ix, int64_t k, int64_t n) {
+    const int mb = ix->mbits_param ? ix->mbits_param : kAutoMantissaBits;
+    if (bf16_only(ix)) return {kFmtBF16, 7};  // the bf16 values are the database
+    if (ix->shadow_param == 1) return {kFmtBF16, mb};
+    if (ix->shadow_param == 2) return {kFmtFP16, 10};
+    const bool rescoring_heavy = k > 0 ? n < 10000 * k : n < (int64_t(1) << 20);
+    if (rescoring_heavy && !ix->fp16_unfit) return {kFmtFP16, 10};
+    return {kFmtBF16, mb};
+}
+
+int query_mbits(const knn_index* ix) {
+    if (ix->shadow_fmt != kFmtBF16) return 10;
+    return bf16_only(ix) ? (ix->mbits_param ? ix->mbits_param : kAutoMantissaBits) : ix->shadow_mbits;
+}
+
+// Rewrites every shadow row from the fp32 master rows (and re-measures the rounding error).
+int convert_shadow(knn_index* ix, ShadowChoice c, cudaStream_t s) {
+    if (ix->ntotal > 0) {
+        KNN_CHECK_CUDA(cudaMemsetAsync(ix->stats, 0, sizeof(DbStats), s));
+        KNN_CHECK(launch_ingest(ix->xb_f32, ix->dp, ix->ntotal, ix->dp, ix->dp, nullptr, ix->xb_h16, c.fmt, c.mbits, false,
+                                nullptr, ix->stats, s));
+        ix->st_shadow_conversions++;
+    }
+    ix->shadow_fmt = c.fmt;
+    ix->shadow_mbits = c.mbits;
+    return KNN_OK;
+}
+
+// Before a tensor-path search for the k best: bring the shadow rows into the format that serves it.  fp16 is only
+// usable while the data sits inside its exponent range: after rows were added (or rewritten) the MEASURED rounding
+// error is compared with what bf16 guarantees (|y - bf16(y)| <= 2^-9 |y|); when fp16 does worse than a quarter of
+// that on the worst row (saturated or flushed values), the automatic choice falls back to bf16 for this database.
+int prepare_shadow(knn_index* ix, int64_t k, cudaStream_t s) {
+    if (bf16_only(ix) || ix->ntotal == 0) return KNN_OK;
+    ShadowChoice want = desired_shadow(ix, k, ix->ntotal);
+    if (want.fmt != ix->shadow_fmt || want.mbits != ix->shadow_mbits) {
+        KNN_CHECK(convert_shadow(ix, want, s));
+        ix->stats_dirty = true;
+    }
+    if (ix->stats_dirty && ix->shadow_fmt == kFmtFP16 && ix->shadow_param == 0) {
+        DbStats h;
+        KNN_CHECK_CUDA(cudaMemcpyAsync(&h, ix->stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        float n2, d2;
+        memcpy(&n2, &h.max_norm2, 4);
+        memcpy(&d2, &h.max_dnorm2, 4);
+        if (d2 > n2 * 9.5367431640625e-07f /* 2^-20 */) {
+            ix->fp16_unfit = true;
+            KNN_CHECK(convert_shadow(ix, desired_shadow(ix, k, ix->ntotal), s));
+        }
+    }
+    ix->stats_dirty = false;
+    return KNN_OK;
 }
 
 // ---- exact path ---------------------------------------------------------------------------
@@ -201,12 +277,12 @@ int search_exact(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D
     KNN_CHECK(ix->lists_i.ensure(size_t(qb) * list_ld * sizeof(uint32_t)));
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
-        KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb, ix->d, ix->dp, ix->xq_f32.as<float>(), nullptr,
+        KNN_CHECK(launch_prep_queries(xq_dev + q0 * ix->d, nb, nb, ix->d, ix->dp, ix->xq_f32.as<float>(), nullptr, kFmtBF16, 7,
                                       ix->xnorm2.as<float>(), ix->eps.as<float>(), ix->stats, ix->metric, s));
         for (int64_t j0 = 0; j0 < N; j0 += chunk) {
             const int64_t j1 = j0 + chunk < N ? j0 + chunk : N;
             KNN_CHECK(launch_scan_f32(ix->xq_f32.as<float>(), ix->xnorm2.as<float>(), nb, ix->dp, ix->xb_f32,
-                                      ix->xb_bf16, ix->ynorm2, j0, j1, ix->metric, ix->scores.as<float>(), chunk, s));
+                                      bf16_rows(ix), ix->ynorm2, j0, j1, ix->metric, ix->scores.as<float>(), chunk, s));
             KNN_CHECK(launch_select_dense(ix->scores.as<float>(), chunk, j1 - j0, nb, seg_len, uint32_t(j0), k, largest,
                                           ix->lists_s.as<float>(), ix->lists_i.as<uint32_t>(), list_ld,
                                           (j0 / seg_len) * k, s));
@@ -226,7 +302,7 @@ int candidate_capacity(int k) {
 
 int tensor_ws_ensure(knn_index::TensorWs& W, int64_t rows, int dp, int cap) {
     KNN_CHECK(W.xq_f32.ensure(size_t(rows) * dp * sizeof(float)));
-    KNN_CHECK(W.xq_bf16.ensure(size_t(rows) * dp * sizeof(__nv_bfloat16)));
+    KNN_CHECK(W.xq_h16.ensure(size_t(rows) * dp * sizeof(h16_t)));
     KNN_CHECK(W.xnorm2.ensure(size_t(rows) * sizeof(float)));
     KNN_CHECK(W.eps.ensure(size_t(rows) * sizeof(float)));
     KNN_CHECK(W.thr.ensure(size_t(rows) * sizeof(float)));
@@ -274,8 +350,9 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     const int ratio = ix->panel_ratio >= 2 ? ix->panel_ratio : (fast_growth ? 8 : 2);
     FilterState st = filter_state(W, off, cap, d_ovf_q);
     float* xq_f32 = W.xq_f32.as<float>() + off * ix->dp;
-    __nv_bfloat16* xq_bf16 = W.xq_bf16.as<__nv_bfloat16>() + off * ix->dp;
-    KNN_CHECK(launch_prep_queries(xq_batch, nb, nb_pad, ix->d, ix->dp, xq_f32, xq_bf16, W.xnorm2.as<float>() + off,
+    h16_t* xq_h16 = W.xq_h16.as<h16_t>() + off * ix->dp;
+    const int fmt_q = ix->shadow_fmt;  // tcgen05.mma kind::f16 takes one 16-bit format per launch (mixing them is an illegal instruction)
+    KNN_CHECK(launch_prep_queries(xq_batch, nb, nb_pad, ix->d, ix->dp, xq_f32, xq_h16, fmt_q, query_mbits(ix), W.xnorm2.as<float>() + off,
                                   W.eps.as<float>() + off, ix->stats, ix->metric, s));
     KNN_CHECK(launch_init_filter(st, nb, nb_pad, int(first_panel), s));
     int64_t j0 = 0;
@@ -292,8 +369,8 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
             e1 = next_event(ix);
             cudaEventRecord(e0, s);
         }
-        KNN_CHECK(gemm_filter_launch(ix->plan, xq_bf16, nb, nb_pad, ix->dp, ix->xb_bf16, N, ix->ynorm2, j0, j1, ix->metric,
-                                     panel == 0, st, s));
+        KNN_CHECK(gemm_filter_launch(ix->plan, xq_h16, fmt_q, nb, nb_pad, ix->dp, ix->xb_h16, ix->shadow_fmt, N, ix->ynorm2, j0, j1,
+                                     ix->metric, panel == 0, st, s));
         if (ix->profile) cudaEventRecord(e1, s);
         ix->st_gemm_launches++;
         KNN_CHECK(launch_tighten(st, W.eps.as<float>() + off, nb, k, 1, nullptr, d_overflow, s));
@@ -312,7 +389,7 @@ int tensor_finish_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     FilterState st = filter_state(W, off, cap);
     if (lower) KNN_CHECK(launch_apply_lower(st.thr, W.eps.as<float>() + off, lower, nb, s));
     KNN_CHECK(launch_rerank(W.xq_f32.as<float>() + off * ix->dp, W.xnorm2.as<float>() + off, nb, ix->dp, ix->xb_f32,
-                            ix->xb_bf16, ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
+                            bf16_rows(ix), ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
     KNN_CHECK(launch_select_final(st.cand_scores, st.cand_ids, st.counts, cap, 0, nb, k, largest, D, I, id_base, s));
     return KNN_OK;
 }
@@ -412,6 +489,7 @@ int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64,
     } else {
         const bool tensor = use_tensor_path(ix, nq, k);
         ix->last_path = tensor ? 2 : 1;
+        if (tensor) KNN_CHECK(prepare_shadow(ix, k, s));
         rc = tensor ? search_tensor(ix, nq, xq_dev, k, D, I, id_base, s) : search_exact(ix, nq, xq_dev, k, D, I, id_base, s);
     }
     if (rc != KNN_OK) return rc;
@@ -528,9 +606,9 @@ int knn_index_free(knn_index* ix) {
                       &ix->overflow, &ix->ovf_q, &ix->ovf_idx, &ix->ovf_x, &ix->ovf_D, &ix->ovf_I, &ix->h_xq, &ix->h_D, &ix->h_I})
         b->release();
     for (knn_index::TensorWs* W : {&ix->ws1, &ix->ws2})
-        for (DevBuf* b : {&W->xq_f32, &W->xq_bf16, &W->xnorm2, &W->eps, &W->thr, &W->counts, &W->cand_s, &W->cand_i}) b->release();
+        for (DevBuf* b : {&W->xq_f32, &W->xq_h16, &W->xnorm2, &W->eps, &W->thr, &W->counts, &W->cand_s, &W->cand_i}) b->release();
     if (ix->xb_f32) cudaFree(ix->xb_f32);
-    if (ix->xb_bf16) cudaFree(ix->xb_bf16);
+    if (ix->xb_h16) cudaFree(ix->xb_h16);
     if (ix->ynorm2) cudaFree(ix->ynorm2);
     if (ix->stats) cudaFree(ix->stats);
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
@@ -545,6 +623,8 @@ int knn_index_reset(knn_index* ix) {
     if (!ix) return KNN_ERR_INVALID;
     DeviceGuard g(ix->device);
     ix->ntotal = 0;
+    ix->stats_dirty = false;
+    ix->fp16_unfit = false;
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->stats, 0, sizeof(DbStats), ix->stream));
     KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
     return KNN_OK;
@@ -567,10 +647,17 @@ int knn_index_add_dev(knn_index* ix, int64_t n, const float* x_dev, void* stream
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     KNN_CHECK(grow(ix, ix->ntotal + n));
     const int64_t r0 = ix->ntotal;
-    KNN_CHECK(launch_ingest(x_dev, n, ix->d, ix->dp, ix->xb_f32 ? ix->xb_f32 + r0 * ix->dp : nullptr,
-                            ix->xb_bf16 + r0 * ix->dp, ix->ynorm2 + r0, ix->stats, s));
+    if (r0 == 0) {  // an empty index takes the format its expected size asks for; later rows follow the rows already there
+        const ShadowChoice c = desired_shadow(ix, 0, std::max<int64_t>(ix->capacity, n));
+        ix->shadow_fmt = c.fmt;
+        ix->shadow_mbits = c.mbits;
+    }
+    KNN_CHECK(launch_ingest(x_dev, ix->d, n, ix->d, ix->dp, ix->xb_f32 ? ix->xb_f32 + r0 * ix->dp : nullptr,
+                            ix->xb_h16 + r0 * ix->dp, ix->shadow_fmt, ix->shadow_mbits, bf16_only(ix), ix->ynorm2 + r0,
+                            ix->stats, s));
     KNN_CHECK_CUDA(cudaEventRecord(ix->add_event, s));
     ix->ntotal += n;
+    ix->stats_dirty = true;
     return KNN_OK;
 }
 
@@ -682,6 +769,7 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
         P.active = true;
         return KNN_OK;
     }
+    KNN_CHECK(prepare_shadow(ix, k, s));
     P.cap = candidate_capacity(k);
     P.qb = round_up(std::min<int64_t>(ix->query_batch, nq), 256);
     P.nbatches = (nq + P.qb - 1) / P.qb;
@@ -763,7 +851,7 @@ int knn_index_reconstruct(knn_index* ix, int64_t i0, int64_t n, float* out) {
                                     size_t(ix->d) * sizeof(float), size_t(n), cudaMemcpyDeviceToHost));
     } else {
         std::vector<uint16_t> tmp(size_t(n) * ix->d);
-        KNN_CHECK_CUDA(cudaMemcpy2D(tmp.data(), size_t(ix->d) * 2, ix->xb_bf16 + i0 * ix->dp, size_t(ix->dp) * 2,
+        KNN_CHECK_CUDA(cudaMemcpy2D(tmp.data(), size_t(ix->d) * 2, ix->xb_h16 + i0 * ix->dp, size_t(ix->dp) * 2,
                                     size_t(ix->d) * 2, size_t(n), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < tmp.size(); ++i) {
             uint32_t u = uint32_t(tmp[i]) << 16;
@@ -799,6 +887,14 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
     else if (n == "small_batch_nq" && value >= 0) ix->small_batch_nq = value;
     else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);
+    else if (n == "shadow_fmt" && value >= 0 && value <= 2) {  // takes effect at the next search (prepare_shadow)
+        if (bf16_only(ix) && value == 2) {
+            set_error("set_param: an index with bf16 storage keeps bf16 rows");
+            return KNN_ERR_INVALID;
+        }
+        ix->shadow_param = int(value);
+    }
+    else if (n == "mantissa_bits" && (value == 0 || (value >= 2 && value <= 7))) ix->mbits_param = int(value);
     else if (n == "tensor_min_nq" && value >= 1) ix->tensor_min_nq = value;
     else if (n == "tensor_min_n" && value >= 1) ix->tensor_min_n = value;
     else {
@@ -818,6 +914,9 @@ int knn_index_get_stat(const knn_index* ix, const char* name, double* out) {
     else if (n == "overflow_batches") *out = double(ix->st_overflow_batches);
     else if (n == "overflow_queries") *out = double(ix->st_overflow_queries);
     else if (n == "capacity") *out = double(ix->capacity);
+    else if (n == "shadow_fmt") *out = ix->shadow_fmt == kFmtFP16 ? 2 : 1;
+    else if (n == "mantissa_bits") *out = ix->shadow_fmt == kFmtFP16 ? 10 : ix->shadow_mbits;
+    else if (n == "shadow_conversions") *out = double(ix->st_shadow_conversions);
     else {
         set_error("get_stat: unknown statistic %s", name);
         return KNN_ERR_INVALID;

@@ -76,19 +76,58 @@ __global__ void __launch_bounds__(kBlock) normalize_l2_kernel(float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
-// One warp per row.  Writes the zero-padded fp32 master row (optional), the bf16 shadow row,
-// |y|^2 and folds max|y|^2, max|y - bf16(y)|^2 into *stats (optional).
-__global__ void __launch_bounds__(kBlock) ingest_rows_kernel(const float* __restrict__ src, int64_t n, int d,
-                                                              int dp, float* __restrict__ dst_f32,
-                                                              __nv_bfloat16* __restrict__ dst_bf16,
+// Rounds v (to nearest, ties to even) to `mbits` explicit mantissa bits; NaN / Inf pass through.
+__device__ __forceinline__ float round_mantissa(float v, int mbits) {
+    uint32_t u = __float_as_uint(v);
+    if ((u & 0x7F800000u) == 0x7F800000u) return v;
+    const int drop = 23 - mbits;
+    u += ((1u << (drop - 1)) - 1u) + ((u >> drop) & 1u);
+    u &= ~((1u << drop) - 1u);
+    return __uint_as_float(u);
+}
+
+// fp32 pair -> packed 16-bit shadow pair + the values the shadow holds.
+// bf16: `mbits` < 7 keeps fewer mantissa bits than the format has (see ShadowFmt in common.cuh: operand bits that
+// never toggle cost no multiplier power, and the kernel is power-bound).
+// fp16: finite values beyond the format's range saturate, values below its normal range flush to zero (no
+// subnormal ever reaches the tensor cores).  Either way the loss shows up in |y - shadow(y)|, which is measured,
+// never assumed.  NaN and Inf pass through unchanged: such a row never enters a result.
+template <int FMT>
+__device__ __forceinline__ uint32_t pack_shadow2(float a, float b, int mbits, float2& back) {
+    if (FMT == kFmtFP16) {
+        const float fa = fabsf(a), fb = fabsf(b);
+        if (fa > 65504.f && fa <= FLT_MAX) a = copysignf(65504.f, a);
+        if (fb > 65504.f && fb <= FLT_MAX) b = copysignf(65504.f, b);
+        if (fa < 6.103515625e-05f) a = 0.f;
+        if (fb < 6.103515625e-05f) b = 0.f;
+        __half2 h = __floats2half2_rn(a, b);
+        back = __half22float2(h);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        if (mbits < 7) {
+            a = round_mantissa(a, mbits);
+            b = round_mantissa(b, mbits);
+        }
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        back = __bfloat1622float2(h);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+// One warp per row.  Writes the zero-padded fp32 master row (optional), the 16-bit shadow row,
+// |y|^2 and folds max|y|^2, max|y - shadow(y)|^2 into *stats (optional).
+template <int FMT>
+__global__ void __launch_bounds__(kBlock) ingest_rows_kernel(const float* __restrict__ src, int64_t src_ld, int64_t n,
+                                                              int d, int dp, float* __restrict__ dst_f32,
+                                                              h16_t* __restrict__ dst_h16,
                                                               float* __restrict__ norms2,
                                                               float* __restrict__ dnorms2, DbStats* stats,
-                                                              int vec_ok, int bf16_is_master) {
+                                                              int vec_ok, int shadow_is_master, int mbits) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = int64_t(gridDim.x) * kWarpsPerBlock;
     float wmax_n = 0.f, wmax_d = 0.f;
     for (int64_t row = int64_t(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5); row < n; row += warps) {
-        const float* r = src + row * int64_t(d);
+        const float* r = src + row * src_ld;
         float s = 0.f, e = 0.f;
         for (int c = lane; c < dp / 4; c += 32) {
             float4 v;
@@ -101,18 +140,16 @@ __global__ void __launch_bounds__(kBlock) ingest_rows_kernel(const float* __rest
                 v.z = c0 + 2 < d ? r[c0 + 2] : 0.f;
                 v.w = c0 + 3 < d ? r[c0 + 3] : 0.f;
             }
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-            __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-            float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
-            if (bf16_is_master) v = make_float4(flo.x, flo.y, fhi.x, fhi.y);  // the rounded values ARE the row
+            float2 flo, fhi;
+            uint2 packed;
+            packed.x = pack_shadow2<FMT>(v.x, v.y, mbits, flo);
+            packed.y = pack_shadow2<FMT>(v.z, v.w, mbits, fhi);
+            if (shadow_is_master) v = make_float4(flo.x, flo.y, fhi.x, fhi.y);  // the rounded values ARE the row
             s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
             float dx = v.x - flo.x, dy = v.y - flo.y, dz = v.z - fhi.x, dw = v.w - fhi.y;
             e = fmaf(dx, dx, e); e = fmaf(dy, dy, e); e = fmaf(dz, dz, e); e = fmaf(dw, dw, e);
             if (dst_f32) reinterpret_cast<float4*>(dst_f32 + row * int64_t(dp))[c] = v;
-            uint2 packed;
-            packed.x = *reinterpret_cast<uint32_t*>(&lo);
-            packed.y = *reinterpret_cast<uint32_t*>(&hi);
-            if (dst_bf16) reinterpret_cast<uint2*>(dst_bf16 + row * int64_t(dp))[c] = packed;
+            if (dst_h16) reinterpret_cast<uint2*>(dst_h16 + row * int64_t(dp))[c] = packed;
         }
         s = warp_sum(s);
         e = warp_sum(e);
@@ -131,7 +168,7 @@ __global__ void __launch_bounds__(kBlock) ingest_rows_kernel(const float* __rest
 }
 
 // eps[q]: bound on |approx score - exact score| for query q against ANY database row, where the
-// approx score is the bf16 x bf16 -> fp32 tensor-core inner product (DESIGN.md "error bound"):
+// approx score is the 16-bit x 16-bit -> fp32 tensor-core inner product (DESIGN.md "error bound"):
 //   |<x^,y^> - <x,y>| <= |dx||y| + |x||dy| + |dx||dy|      (Cauchy-Schwarz, dx = x^ - x)
 // plus a slack of dp * 2^-22 * |x||y| for the fp32 accumulation inside the MMA and the rerank.
 __global__ void query_eps_kernel(const float* __restrict__ xnorm2, const float* dnorm2, int64_t nq, int dp,
@@ -354,27 +391,35 @@ int launch_normalize_l2(float* x, int64_t n, int64_t d, cudaStream_t s) {
     return KNN_OK;
 }
 
-int launch_ingest(const float* src, int64_t n, int d, int dp, float* dst_f32, __nv_bfloat16* dst_bf16,
-                  float* norms2, DbStats* stats, cudaStream_t s) {
+int launch_ingest(const float* src, int64_t src_ld, int64_t n, int d, int dp, float* dst_f32, h16_t* dst_h16, int fmt,
+                  int mbits, bool shadow_is_master, float* norms2, DbStats* stats, cudaStream_t s) {
     if (n <= 0) return KNN_OK;
-    const int vec_ok = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
-    ingest_rows_kernel<<<grid_for_rows(n, kWarpsPerBlock, 8), kBlock, 0, s>>>(src, n, d, dp, dst_f32, dst_bf16,
-                                                                               norms2, nullptr, stats, vec_ok, dst_f32 == nullptr);
+    const int vec_ok = (d % 4 == 0) && (src_ld % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
+    const int grid = grid_for_rows(n, kWarpsPerBlock, 8);
+    if (fmt == kFmtFP16)
+        ingest_rows_kernel<kFmtFP16><<<grid, kBlock, 0, s>>>(src, src_ld, n, d, dp, dst_f32, dst_h16, norms2, nullptr, stats,
+                                                            vec_ok, shadow_is_master, mbits);
+    else
+        ingest_rows_kernel<kFmtBF16><<<grid, kBlock, 0, s>>>(src, src_ld, n, d, dp, dst_f32, dst_h16, norms2, nullptr, stats,
+                                                            vec_ok, shadow_is_master, mbits);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }
 
 int launch_prep_queries(const float* xq, int64_t nq, int64_t nq_pad, int d, int dp, float* xq_f32,
-                        __nv_bfloat16* xq_bf16, float* xnorm2, float* eps, const DbStats* stats, int metric,
+                        h16_t* xq_h16, int fmt, int mbits, float* xnorm2, float* eps, const DbStats* stats, int metric,
                         cudaStream_t s) {
     if (nq <= 0) return KNN_OK;
     // eps doubles as scratch for |dx|^2 until query_eps_kernel overwrites it
     const int vec_ok = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(xq) % 16 == 0);
-    ingest_rows_kernel<<<grid_for_rows(nq, kWarpsPerBlock, 8), kBlock, 0, s>>>(xq, nq, d, dp, xq_f32, xq_bf16,
-                                                                                xnorm2, eps, nullptr, vec_ok, 0);
+    const int grid = grid_for_rows(nq, kWarpsPerBlock, 8);
+    if (fmt == kFmtFP16)
+        ingest_rows_kernel<kFmtFP16><<<grid, kBlock, 0, s>>>(xq, d, nq, d, dp, xq_f32, xq_h16, xnorm2, eps, nullptr, vec_ok, 0, mbits);
+    else
+        ingest_rows_kernel<kFmtBF16><<<grid, kBlock, 0, s>>>(xq, d, nq, d, dp, xq_f32, xq_h16, xnorm2, eps, nullptr, vec_ok, 0, mbits);
     KNN_CHECK_LAUNCH();
-    if (xq_bf16 && nq_pad > nq) {
-        KNN_CHECK_CUDA(cudaMemsetAsync(xq_bf16 + nq * int64_t(dp), 0, size_t(nq_pad - nq) * dp * sizeof(__nv_bfloat16), s));
+    if (xq_h16 && nq_pad > nq) {
+        KNN_CHECK_CUDA(cudaMemsetAsync(xq_h16 + nq * int64_t(dp), 0, size_t(nq_pad - nq) * dp * sizeof(h16_t), s));
     }
     query_eps_kernel<<<int((nq + 255) / 256), 256, 0, s>>>(xnorm2, eps, nq, dp, stats, metric, eps);
     KNN_CHECK_LAUNCH();

@@ -130,16 +130,80 @@ class PeerExchange:
         self._release()
 
 
-def shard_bounds(n: int, world: int):
-    """Contiguous near-equal row ranges: rank r owns [b[r], b[r+1])."""
-    return [(n * r) // world for r in range(world + 1)]
+def shard_bounds(n: int, world: int, weights=None):
+    """Contiguous row ranges: rank r owns [b[r], b[r+1]).  Near-equal by default; with ``weights`` (one positive
+    number per rank, e.g. measured_rank_speeds) rank r gets a share of the rows proportional to weights[r]."""
+    if weights is None:
+        return [(n * r) // world for r in range(world + 1)]
+    w = [float(v) for v in weights]
+    if len(w) != world or min(w) <= 0:
+        raise ValueError("weights: one positive number per rank")
+    total, acc, b = sum(w), 0.0, [0]
+    for r in range(world - 1):
+        acc += w[r]
+        b.append(max(b[-1], min(n, int(round(n * acc / total)))))
+    b.append(n)
+    return b
+
+
+def measured_rank_speeds(d: int, device: int, group=None, seconds: float = 1.5, rows: int = 1 << 20, queries: int = 16384,
+                         spread: float = 0.15):
+    """Relative speed of every rank's GPU on the engine's own dominant kernel, for speed-proportional sharding.
+
+    A search step ends when the SLOWEST shard is done (the bound exchange and the merge are collectives), and under a
+    board power cap the chips of one box do not run the tensor cores at the same clock.  All ranks run the same
+    synthetic search (``rows`` x ``queries``, k = 100) simultaneously for ``seconds`` - long enough for the clocks to
+    settle under the cap - and the pairs/s of the second half are all-gathered.  Returns one weight per rank with mean
+    1, clipped to 1 +- ``spread``.  Collective over ``group``; every rank gets the same list."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from .index import IndexFlat, normalize_L2
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [1.0]
+    dev = torch.device("cuda", device)
+    g = torch.Generator(device=dev).manual_seed(99)
+    idx = IndexFlat(d, 0, device=device)
+    idx.set_param("path", 2)
+    idx.reserve(rows)
+    for i in range(0, rows, 1 << 18):
+        x = torch.randn(min(1 << 18, rows - i), d, device=dev, generator=g)
+        normalize_L2(x)
+        idx.add(x)
+    xq = torch.randn(queries, d, device=dev, generator=g)
+    normalize_L2(xq)
+    idx.search(xq, 100)
+    torch.cuda.synchronize(dev)
+    dist.barrier(group=group)
+    t0 = time.perf_counter()
+    done, half_t, half_n = 0, None, 0
+    while True:
+        idx.search(xq, 100)
+        torch.cuda.synchronize(dev)
+        done += 1
+        t = time.perf_counter() - t0
+        if half_t is None and t >= seconds / 2:
+            half_t, half_n = t, done
+        if t >= seconds and half_t is not None and done > half_n:
+            break
+    rate = (done - half_n) / (t - half_t)
+    rates = torch.zeros(world, device=dev, dtype=torch.float64)
+    dist.all_gather_into_tensor(rates, torch.tensor([rate], device=dev, dtype=torch.float64), group=group)
+    del idx
+    r = rates.tolist()
+    mean = sum(r) / world
+    return [min(1.0 + spread, max(1.0 - spread, v / mean)) for v in r]
 
 
 class ShardedIndexFlat:
     TWO_PHASE_MAX_QUERIES = 131072  # limit of knn_index_search_filter_dev (candidate lists stay resident)
 
     def __init__(self, d: int, metric: int, group=None, device=None, index_factory=None, merge_fn=None,
-                 exchange_bounds: bool = True, peer_merge: bool = True, **index_kw):
+                 exchange_bounds: bool = True, peer_merge: bool = True, shard_weights=None, **index_kw):
         import torch.distributed as dist
 
         self._dist = dist
@@ -165,6 +229,8 @@ class ShardedIndexFlat:
         self.last_stats = None
         self.local = index_factory()
         self._merge = merge_fn
+        # share of the rows every rank keeps (None: equal shares; see measured_rank_speeds)
+        self.shard_weights = list(shard_weights) if shard_weights is not None else None
         # one (global_start, local_start, count) triple per add() call
         self._segments = []
         self._ntotal = 0
@@ -181,7 +247,7 @@ class ShardedIndexFlat:
         """Every rank passes the same rows (as the reference's drivers would); rank r keeps its
         contiguous slice.  Global id of a row = its position in the concatenation of all adds."""
         n = x.shape[0]
-        b = shard_bounds(n, self.world)
+        b = shard_bounds(n, self.world, self.shard_weights)
         lo, hi = b[self.rank], b[self.rank + 1]
         self.add_local(x[lo:hi], global_start=self._ntotal + lo, n_global=n)
 

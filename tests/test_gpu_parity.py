@@ -199,15 +199,21 @@ TENSOR_CASES = [
 ]
 
 
+BF16, FP16 = 1, 2  # values of the "shadow_fmt" parameter (0 = automatic)
+
+
+@pytest.mark.parametrize("fmt", [BF16, FP16])
 @pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("metric", [IP, L2])
 @pytest.mark.parametrize("case", TENSOR_CASES)
-def test_tensor_path_parity(knn, case, metric, cta_group):
-    """cta_group 1: one CTA per 128x256 tile; 2: CTA pairs on 256x256 tiles (tcgen05 cta_group::2)."""
+def test_tensor_path_parity(knn, case, metric, cta_group, fmt):
+    """cta_group 1: one CTA per 128x256 tile; 2: CTA pairs on 256x256 tiles (tcgen05 cta_group::2).
+    fmt: 16-bit format of the tensor-core operands (bf16 or fp16 shadow rows and queries)."""
     nq, nb, d, k, qb = case
     xq, xb = _data(nq, nb, d, seed=7 * nq + nb, normalize=metric == IP, scale=1.7)
-    D, I, idx = _search(knn, xq, xb, k, metric, path=2, query_batch=qb, cta_group=cta_group)
+    D, I, idx = _search(knn, xq, xb, k, metric, path=2, query_batch=qb, cta_group=cta_group, shadow_fmt=fmt)
     assert idx.stat("path") == 2 and idx.stat("gemm_launches") >= 1
+    assert idx.stat("shadow_fmt") == fmt
     assert idx.stat("overflow_batches") == 0
     D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
     # L2 on unnormalised rows: |x|^2+|y|^2 ~ 6000, so the fp32 expansion formula resolves distances to
@@ -357,6 +363,137 @@ def test_bf16_storage_index(knn):
         D, I = idx.search(xq, 50)
         D_ref, I_ref = fo.knn_flat(xq, xb_r, 50, IP)
         check_parity(D, I, D_ref, I_ref, xq, xb_r, IP, max_excused_frac=2e-3)
+
+
+def test_shadow_format_is_chosen_from_the_data(knn):
+    """fp16 shadow rows while the data sits inside fp16's range (3 more mantissa bits than bf16 -> smaller error
+    bound -> fewer candidates to rescore); data outside it (saturating or flushing to zero) is noticed through the
+    MEASURED rounding error and the shadow rewritten in bf16.  The result is the exact one either way."""
+    k = 20
+    for scale, want in [(1.0, FP16), (3e5, BF16), (2e-7, BF16)]:
+        xq, xb = _data(150, 12000, 128, seed=21, normalize=False, scale=scale)
+        D, I, idx = _search(knn, xq, xb, k, IP, path=2)
+        assert idx.stat("shadow_fmt") == want, (scale, idx.stat("shadow_fmt"))
+        assert idx.stat("shadow_conversions") == (0 if want == FP16 else 1)
+        assert idx.stat("overflow_batches") == 0
+        D1, I1, _ = _search(knn, xq, xb, k, IP, path=1)
+        assert np.array_equal(I, I1) and np.array_equal(D, D1)
+    # rows that leave the range arrive later: the next search converts, once
+    xq, xb = _data(100, 10000, 64, seed=22, normalize=False)
+    idx = knn.IndexFlat(64, L2)
+    idx.set_param("path", 2)
+    idx.add(xb)
+    idx.search(xq, 5)
+    assert idx.stat("shadow_fmt") == FP16
+    big = (xb[:500] * 1e6).astype(np.float32)
+    idx.add(big)
+    D, I = idx.search(xq, 5)
+    assert idx.stat("shadow_fmt") == BF16 and idx.stat("shadow_conversions") == 1
+    idx.add(xb[:10])
+    idx.search(xq, 5)
+    assert idx.stat("shadow_conversions") == 1  # stays bf16
+    all_rows = np.concatenate([xb, big])
+    D_ref, I_ref = fo.knn_flat(xq, all_rows, 5, L2)
+    check_parity(D, I, D_ref, I_ref, xq, all_rows, L2, max_excused_frac=1e-2)
+    idx.reset()
+    idx.add(xb)
+    idx.search(xq, 5)
+    assert idx.stat("shadow_fmt") == FP16  # a fresh database decides afresh
+
+
+def test_shadow_format_switch_and_forced_fp16_out_of_range(knn):
+    """set_param("shadow_fmt") on a filled index rewrites the shadow from the fp32 master rows; every format gives the
+    same bits (the rerank is exact).  fp16 forced onto out-of-range data saturates, the error bound explodes, the
+    candidate lists overflow and the exact scan answers: slow, never wrong."""
+    xq, xb = _data(130, 15000, 256, seed=23)
+    idx = knn.IndexFlat(256, IP)
+    idx.set_param("path", 2)
+    idx.add(xb)
+    res = {}
+    for fmt in (FP16, BF16, FP16):
+        idx.set_param("shadow_fmt", fmt)
+        res[fmt] = idx.search(xq, 30)
+        assert idx.stat("shadow_fmt") == fmt
+    assert idx.stat("shadow_conversions") == 2
+    assert np.array_equal(res[FP16][1], res[BF16][1]) and np.array_equal(res[FP16][0], res[BF16][0])
+    D_ref, I_ref = fo.knn_flat(xq, xb, 30, IP)
+    check_parity(res[FP16][0], res[FP16][1], D_ref, I_ref, xq, xb, IP, max_excused_frac=2e-3)
+    xq, xb = _data(64, 9000, 64, seed=24, normalize=False, scale=3e5)
+    D, I, idx = _search(knn, xq, xb, 7, IP, path=2, shadow_fmt=FP16)
+    assert idx.stat("shadow_fmt") == FP16
+    D1, I1, _ = _search(knn, xq, xb, 7, IP, path=1)
+    assert np.array_equal(I, I1) and np.array_equal(D, D1)
+
+
+def test_shadow_format_follows_the_search_regime(knn):
+    """Automatic choice: fp16 operands where the exact rescoring dominates (k large against n), bf16 where the GEMM
+    does (fp16 costs tensor-core power); the shadow rows are rewritten from the fp32 rows when a search asks for the
+    other regime.  Same bits either way."""
+    xq, xb = _data(120, 30000, 128, seed=27)
+    idx = knn.IndexFlat(128, IP)
+    idx.set_param("path", 2)
+    idx.add(xb)
+    idx_exact = knn.IndexFlat(128, IP)
+    idx_exact.set_param("path", 1)
+    idx_exact.add(xb)
+    for k, want, conversions in [(2, BF16, 1), (2, BF16, 1), (5, FP16, 2), (100, FP16, 2), (3, BF16, 3)]:
+        D, I = idx.search(xq, k)
+        assert (idx.stat("shadow_fmt"), idx.stat("shadow_conversions")) == (want, conversions), k
+        D1, I1 = idx_exact.search(xq, k)
+        assert np.array_equal(I, I1) and np.array_equal(D, D1)
+    big = knn.IndexFlat(128, IP)   # the expected size is known up front: no rewrite
+    big.reserve(1 << 21)
+    big.add(xb)
+    assert big.stat("shadow_fmt") == BF16
+
+
+@pytest.mark.parametrize("bits", [3, 5, 6])
+def test_bf16_operands_with_fewer_mantissa_bits(knn, bits):
+    """"mantissa_bits": bf16 operands rounded to fewer mantissa bits (operand bits that never toggle cost no
+    multiplier power).  The rounding error is measured, the bound grows with it, the result stays exact."""
+    xq, xb = _data(200, 25000, 512, seed=28)
+    D, I, idx = _search(knn, xq, xb, 50, IP, path=2, shadow_fmt=BF16, mantissa_bits=bits)
+    assert idx.stat("mantissa_bits") == bits
+    assert bits < 5 or idx.stat("overflow_batches") == 0  # 3 bits: the bound is so wide that lists overflow -> exact scan
+    D1, I1, _ = _search(knn, xq, xb, 50, IP, path=1)
+    assert np.array_equal(I, I1) and np.array_equal(D, D1)
+    import torch
+
+    idx = knn.IndexFlat(512, L2, bf16_storage=True)  # queries only: the bf16 rows are the database
+    idx.set_param("mantissa_bits", bits)
+    with pytest.raises(ValueError):
+        idx.set_param("shadow_fmt", FP16)
+    idx.add(xb)
+    res = {}
+    for path in (2, 1):
+        idx.set_param("path", path)
+        res[path] = idx.search(xq, 20)
+    assert np.array_equal(res[1][1], res[2][1]) and np.array_equal(res[1][0], res[2][0])
+    xb_r = torch.from_numpy(xb).to(torch.bfloat16).to(torch.float32).numpy()
+    D_ref, I_ref = fo.knn_flat(xq, xb_r, 20, L2)
+    check_parity(res[2][0], res[2][1], D_ref, I_ref, xq, xb_r, L2, max_excused_frac=2e-3)
+
+
+@pytest.mark.parametrize("fmt", [BF16, FP16])
+@pytest.mark.parametrize("path", [1, 2])
+def test_nan_rows_never_enter_a_result(knn, path, fmt):
+    """Like faiss's heap (a NaN score never beats the heap top), a row holding a NaN is never returned - and must
+    not disturb the candidate threshold of the tensor path either."""
+    xq, xb = _data(100, 12000, 128, seed=26)
+    bad = np.arange(0, 12000, 37)
+    xb_nan = xb.copy()
+    xb_nan[bad, 5] = np.nan
+    D, I, _ = _search(knn, xq, xb_nan, 25, IP, path=path, shadow_fmt=fmt)
+    keep = np.setdiff1d(np.arange(12000), bad)
+    D_ref, I_ref = fo.knn_flat(xq, xb[keep], 25, IP)
+    check_parity(D, keep_inverse(I, keep), D_ref, I_ref, xq, xb[keep], IP, max_excused_frac=2e-3)
+    assert not np.isin(I, bad).any() and np.isfinite(D).all()
+
+
+def keep_inverse(I, keep):
+    inv = np.full(int(keep.max()) + 1, -1, dtype=np.int64)
+    inv[keep] = np.arange(len(keep))
+    return inv[I]
 
 
 def test_torch_device_api_and_merge(knn):

@@ -48,7 +48,7 @@ def _merge_numpy(Dg, Ig, metric):
     return torch.from_numpy(outD), torch.from_numpy(outI)
 
 
-def _worker(rank, world, port, metric, out):
+def _worker(rank, world, port, metric, weights, out):
     sys.path.insert(0, str(REPO))
     sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -59,12 +59,16 @@ def _worker(rank, world, port, metric, out):
     rng = np.random.default_rng(0)
     xb = rng.standard_normal((1001, 32)).astype(np.float32)
     xq = rng.standard_normal((17, 32)).astype(np.float32)
-    index = ShardedIndexFlat(32, metric, index_factory=lambda: _OracleShard(32, metric), merge_fn=_merge_numpy)
+    index = ShardedIndexFlat(32, metric, index_factory=lambda: _OracleShard(32, metric), merge_fn=_merge_numpy,
+                             shard_weights=weights)
     index.add(xb[:300])      # three adds: ids must stay positions in the concatenation
     index.add(xb[300:301])
     index.add(xb[301:])
     assert index.ntotal == 1001
-    assert index.local.ntotal in (500, 501)
+    if weights is None:
+        assert index.local.ntotal in (500, 501)
+    else:  # speed-proportional shards: rank 0 keeps ~30 % of every add
+        assert abs(index.local.ntotal - 1001 * weights[rank] / sum(weights)) <= 2
     for k in (5, 1001 // 2, 1200):  # last one: k > ntotal -> -1 padding survives the merge
         D, I = index.search(xq, k)
         D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
@@ -80,14 +84,14 @@ def _worker(rank, world, port, metric, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("metric", [0, 1])
-def test_sharded_index_world2_gloo(tmp_path, metric):
+@pytest.mark.parametrize("metric,weights", [(0, None), (1, None), (0, [0.6, 1.4])])
+def test_sharded_index_world2_gloo(tmp_path, metric, weights):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     out = tmp_path / "ok"
-    mp.spawn(_worker, args=(2, port, metric, str(out)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, metric, weights, str(out)), nprocs=2, join=True)
     assert out.read_text() == "ok"
 
 
@@ -100,3 +104,18 @@ def test_shard_bounds_cover_everything():
             b = shard_bounds(n, w)
             assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
             assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) <= 1
+
+
+def test_weighted_shard_bounds():
+    sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
+    from knn_b200.distributed import shard_bounds
+
+    assert shard_bounds(1000, 4, [1, 1, 1, 1]) == [0, 250, 500, 750, 1000]
+    b = shard_bounds(10_000_000, 8, [1.0, 0.92, 1.03, 1.0, 1.05, 0.97, 1.01, 1.02])
+    sizes = [y - x for x, y in zip(b, b[1:])]
+    assert b[0] == 0 and b[-1] == 10_000_000 and min(sizes) == sizes[1] and max(sizes) == sizes[4]
+    assert abs(sizes[1] / sizes[4] - 0.92 / 1.05) < 1e-4
+    assert shard_bounds(3, 4, [5, 1, 1, 1])[-1] == 3
+    for bad in ([1, 1], [1, 0, 1, 1]):
+        with pytest.raises(ValueError):
+            shard_bounds(10, 4, bad)

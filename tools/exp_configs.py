@@ -17,6 +17,9 @@ import torch
 import knn_b200
 
 dev = torch.device("cuda:0")
+# 16-bit operand format: "fmt=1" forces bf16 shadow rows, "fmt=2" fp16 (0 = automatic); "mbits=5" keeps 5 mantissa bits in bf16
+OPTS = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+SHADOW_FMT, MBITS = int(OPTS.get("fmt", 0)), int(OPTS.get("mbits", 0))
 
 
 def rows(n, d, seed, clustered=0):
@@ -35,6 +38,9 @@ def run(name, xb, xq, k, metric, normalize=True, bf16_storage=False, reps=3):
             knn_b200.normalize_L2(xq)
     t0 = time.perf_counter()
     idx = knn_b200.IndexFlat(xb.shape[1], metric, bf16_storage=bf16_storage)
+    if SHADOW_FMT and not bf16_storage:
+        idx.set_param("shadow_fmt", SHADOW_FMT)
+    idx.set_param("mantissa_bits", MBITS)
     idx.reserve(xb.shape[0])
     for i in range(0, xb.shape[0], 1 << 20):
         idx.add(xb[i:i + (1 << 20)])
@@ -55,12 +61,12 @@ def run(name, xb, xq, k, metric, normalize=True, bf16_storage=False, reps=3):
     flop = 2.0 * xq.shape[0] * xb.shape[0] * xb.shape[1]
     print(json.dumps(dict(config=name, rows=xb.shape[0], queries=xq.shape[0], k=k, metric="IP" if metric == 0 else "L2",
                           ms=round(ms, 2), qps=round(xq.shape[0] / ms * 1e3, 1), tflops_equiv=round(flop / ms / 1e9, 1),
-                          path=path, overflow_batches=overflow, identical_to_exact_path_on_sample=same,
+                          path=path, overflow_batches=overflow, shadow_fmt=int(idx.stat("shadow_fmt")), mantissa_bits=int(idx.stat("mantissa_bits")), identical_to_exact_path_on_sample=same,
                           build_s=round(build_s, 3))), flush=True)
     del idx
 
 
-which = sys.argv[1:] or ["C2", "C3", "C5"]
+which = [a for a in sys.argv[1:] if "=" not in a] or ["C2", "C3", "C5"]
 if "C2" in which:
     x = rows(14433, 1024, 1, clustered=5125)
     run("C2 k=11 cosine", x.clone(), None or x.clone(), 11, 0)
