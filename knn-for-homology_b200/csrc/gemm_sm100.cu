@@ -666,6 +666,10 @@ int gemm_filter_launch(GemmPlan* p, const h16_t* xq_h16, int fmt_q, int64_t nq, 
     a.debug_skip_epilogue = p->debug_skip_epilogue;
     a.idesc = cg == 1 ? Cfg<1>::instr_desc(fmt_q, fmt_db) : Cfg<2>::instr_desc(fmt_q, fmt_db);
     a.stages = cg == 1 ? Cfg<1>::kStages : Cfg<2>::kStages;
+    // Few query tiles: the kernel is the bandwidth kernel of small batches (the database streams by once) and what
+    // limits it is bytes in flight - half of every stage is the re-loaded query tile.  6 stages instead of 4:
+    // 5.3 -> 5.8 TB/s at nq = 1, 4.5 -> 4.8 TB/s at nq = 256 (profiles/r01_small_batch.md); equal for large batches.
+    if (cg == 2 && a.m_tiles <= 4) a.stages = kMaxStages;
     if (p->stages >= 2 && p->stages <= (cg == 1 ? 4 : kMaxStages)) a.stages = p->stages;
     a.hint_q = p->l2_hints ? kEvictLast : kEvictNormal;
     a.hint_db = p->l2_hints ? kEvictFirst : kEvictNormal;

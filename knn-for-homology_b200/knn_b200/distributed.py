@@ -329,9 +329,10 @@ class ShardedIndexFlat:
             j = -(-k // self.world)
             lower, lower_j = self.local.search_filter(xd, k, j)
             mark("filter")
-            self._dist.all_reduce(lower, op=self._dist.ReduceOp.MAX, group=self.group)
-            self._dist.all_reduce(lower_j, op=self._dist.ReduceOp.MIN, group=self.group)
-            lower = torch.maximum(lower, lower_j)
+            # one collective for both: MAX over the shards of lower, MIN of lower_j = -MAX(-lower_j)
+            both = torch.stack([lower, -lower_j])
+            self._dist.all_reduce(both, op=self._dist.ReduceOp.MAX, group=self.group)
+            lower = torch.maximum(both[0], -both[1])
             mark("all_reduce_bounds")
             D, I = self.local.search_finish(lower, k)
             mark("finish")
