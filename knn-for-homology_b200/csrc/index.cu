@@ -124,12 +124,28 @@ struct knn_index {
     // statistics of the last search
     int last_path = 0;
     long long st_launches = 0, st_gemm_launches = 0, st_candidates = 0, st_overflow_batches = 0, st_overflow_queries = 0, st_rerank_pairs = 0, st_shadow_conversions = 0;
-    double st_gemm_ms = 0;
-    std::vector<cudaEvent_t> ev_pool;
+    double st_gemm_ms = 0, st_rerank_ms = 0;
+    std::vector<cudaEvent_t> ev_pool;   // profile = 1: pairs of events around the GEMM launches ...
     size_t ev_used = 0;
+    std::vector<cudaEvent_t> ev_pool_r; // ... and around the rerank launches
+    size_t ev_used_r = 0;
 };
 
 namespace {
+
+// profile = 1: after the stream has been synchronised, fold the event pairs into the statistics
+void collect_profile(knn_index* ix) {
+    for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ix->ev_pool[i], ix->ev_pool[i + 1]);
+        ix->st_gemm_ms += ms;
+    }
+    for (size_t i = 0; i + 1 < ix->ev_used_r; i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ix->ev_pool_r[i], ix->ev_pool_r[i + 1]);
+        ix->st_rerank_ms += ms;
+    }
+}
 
 bool bf16_only(const knn_index* ix) { return (ix->flags & KNN_FLAG_BF16_STORAGE) != 0; }
 
@@ -174,6 +190,15 @@ int grow(knn_index* ix, int64_t want_rows, bool exact = false) {
     ix->ynorm2 = nn;
     ix->capacity = cap;
     return KNN_OK;
+}
+
+cudaEvent_t next_event_r(knn_index* ix) {
+    if (ix->ev_used_r == ix->ev_pool_r.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ix->ev_pool_r.push_back(e);
+    }
+    return ix->ev_pool_r[ix->ev_used_r++];
 }
 
 cudaEvent_t next_event(knn_index* ix) {
@@ -388,8 +413,10 @@ int tensor_finish_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     const int largest = ix->metric == KNN_METRIC_INNER_PRODUCT;
     FilterState st = filter_state(W, off, cap);
     if (lower) KNN_CHECK(launch_apply_lower(st.thr, W.eps.as<float>() + off, lower, nb, s));
+    if (ix->profile) cudaEventRecord(next_event_r(ix), s);
     KNN_CHECK(launch_rerank(W.xq_f32.as<float>() + off * ix->dp, W.xnorm2.as<float>() + off, nb, ix->dp, ix->xb_f32,
                             bf16_rows(ix), ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
+    if (ix->profile) cudaEventRecord(next_event_r(ix), s);
     KNN_CHECK(launch_select_final(st.cand_scores, st.cand_ids, st.counts, cap, 0, nb, k, largest, D, I, id_base, s));
     return KNN_OK;
 }
@@ -475,6 +502,8 @@ int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64,
     const long long launches0 = g_launches.load();
     ix->st_gemm_launches = 0;
     ix->st_gemm_ms = 0;
+    ix->st_rerank_ms = 0;
+    ix->ev_used_r = 0;
     ix->st_overflow_batches = 0;
     ix->st_overflow_queries = 0;
     ix->ev_used = 0;
@@ -495,11 +524,7 @@ int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64,
     if (rc != KNN_OK) return rc;
     if (ix->profile && ix->ev_used) {
         KNN_CHECK_CUDA(cudaStreamSynchronize(s));
-        for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ix->ev_pool[i], ix->ev_pool[i + 1]);
-            ix->st_gemm_ms += ms;
-        }
+        collect_profile(ix);
     }
     ix->st_launches = g_launches.load() - launches0;
     return KNN_OK;
@@ -612,6 +637,7 @@ int knn_index_free(knn_index* ix) {
     if (ix->ynorm2) cudaFree(ix->ynorm2);
     if (ix->stats) cudaFree(ix->stats);
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ix->ev_pool_r) cudaEventDestroy(e);
     if (ix->add_event) cudaEventDestroy(ix->add_event);
     if (ix->plan) gemm_plan_destroy(ix->plan);
     if (ix->stream) cudaStreamDestroy(ix->stream);
@@ -754,6 +780,8 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->add_event, 0));
     ix->st_gemm_launches = 0;
     ix->st_gemm_ms = 0;
+    ix->st_rerank_ms = 0;
+    ix->ev_used_r = 0;
     ix->st_overflow_batches = 0;
     ix->st_overflow_queries = 0;
     ix->ev_used = 0;
@@ -828,11 +856,7 @@ int knn_index_search_finish_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     KNN_CHECK(redo_overflowed(ix, nq, P.qb, P.nbatches, xq_dev, P.k, D_dev, I_dev, id_base, s));
     if (ix->profile && ix->ev_used) {
         KNN_CHECK_CUDA(cudaStreamSynchronize(s));
-        for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ix->ev_pool[i], ix->ev_pool[i + 1]);
-            ix->st_gemm_ms += ms;
-        }
+        collect_profile(ix);
     }
     ix->st_launches = g_launches.load() - launches0;
     return KNN_OK;
@@ -911,6 +935,7 @@ int knn_index_get_stat(const knn_index* ix, const char* name, double* out) {
     else if (n == "launches") *out = double(ix->st_launches);
     else if (n == "gemm_launches") *out = double(ix->st_gemm_launches);
     else if (n == "gemm_ms") *out = ix->st_gemm_ms;
+    else if (n == "rerank_ms") *out = ix->st_rerank_ms;
     else if (n == "overflow_batches") *out = double(ix->st_overflow_batches);
     else if (n == "overflow_queries") *out = double(ix->st_overflow_queries);
     else if (n == "capacity") *out = double(ix->capacity);

@@ -77,9 +77,13 @@ def _worker(rank, world, port, out):
     xq = rng.standard_normal((301, 64)).astype(np.float32)
     for metric in (0, 1):
         # gloo moves no CUDA tensors here: the bound exchange (an all-reduce of device tensors) stays off
-        index = ShardedIndexFlat(64, metric, device=0, exchange_bounds=False, peer_merge=True)
+        # metric 1 also runs with speed-proportional (unequal) shards: placement must not change the result
+        index = ShardedIndexFlat(64, metric, device=0, exchange_bounds=False, peer_merge=True,
+                                 shard_weights=[0.7, 1.3] if metric == 1 else None)
         index.add(xb[:7000])
         index.add(xb[7000:])
+        if metric == 1:
+            assert abs(index.local.ntotal - 20011 * (0.35 if rank == 0 else 0.65)) <= 2
         single = knn_b200.IndexFlat(64, metric, device=0)
         single.add(xb)
         xq_d = torch.from_numpy(xq).cuda()
