@@ -147,6 +147,7 @@ void gemm_plan_set_cta_group(GemmPlan* p, int cg);          // 1 or 2 (default 2
 void gemm_plan_set_l2_hints(GemmPlan* p, int on);
 void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue);
 void gemm_plan_set_stages(GemmPlan* p, int stages);
+void gemm_plan_set_stream_kernel(GemmPlan* p, int on);   // few-queries variant for launches with <= 64 queries (default on)
 int gemm_plan_query_rows_multiple(const GemmPlan* p);     // nq_pad granularity of the chosen variant
 // Scores queries (16-bit, format fmt_q, [nq_pad x dp]) against database rows [j0, j1) (16-bit, format fmt_db,
 // [ntotal x dp]) on the tensor cores and appends every (score, id) with score >= thr[q] to the candidate lists.

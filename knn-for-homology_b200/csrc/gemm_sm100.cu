@@ -540,6 +540,185 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
 }
 
+// =============================================================================================
+// Few-queries variant (<= 64 queries per launch): the roles of the operands are swapped.  The database rows are the
+// M = 128 operand and stream through a deep TMA ring, 16 KB per stage, ALL of it database bytes; the queries are the
+// N operand (NQT = 32 or 64 rows) and stay resident in shared memory for the whole launch.  With one query tile the
+// main kernel re-loads the query tile into every stage (half of its bytes in flight) and spends a 256 x 256 MMA on
+// a handful of queries; here a launch is a pure stream of the 16-bit rows: the bandwidth kernel of the path.
+// Accumulator: 128 TMEM lanes = database rows, NQT columns = queries; an epilogue thread owns one database row and
+// compares its NQT scores with the per-query thresholds (shared memory).
+constexpr int SBM = 128;            // database rows per tile
+constexpr int kStreamAcc = 4;       // accumulator stages of NQT columns
+constexpr int kStreamTmemCols = 256;
+constexpr int kStreamMaxStages = 10;
+constexpr uint32_t kStreamBytesA = SBM * BK * 2;
+
+struct StreamBarriers {
+    uint64_t full[kStreamMaxStages];
+    uint64_t empty[kStreamMaxStages];
+    uint64_t acc_full[kStreamAcc];
+    uint64_t acc_empty[kStreamAcc];
+    uint64_t queries;
+    uint32_t tmem_base;
+};
+
+static size_t stream_smem_bytes(int nqt, int num_kb, int stages) {
+    return 1024 /*align slack*/ + size_t(num_kb) * nqt * BK * 2 + size_t(stages) * kStreamBytesA + sizeof(StreamBarriers) + 64 * sizeof(float) + 64;
+}
+
+template <int NQT, bool L2, bool DENSE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int nstages = args.stages;
+    const uint32_t bytes_q_kb = NQT * BK * 2;                       // one K block of the resident queries
+    uint8_t* smem_q = smem;                                         // [num_kb][NQT x 64] 128-byte swizzled
+    uint8_t* smem_a = smem + size_t(args.num_kb) * bytes_q_kb;      // [nstages][128 x 64]
+    StreamBarriers* bars = reinterpret_cast<StreamBarriers*>(smem_a + size_t(nstages) * kStreamBytesA);
+    float* thr_s = reinterpret_cast<float*>(bars + 1);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = args.n_tiles;  // tiles of 128 database rows
+    // instruction descriptor: M = 128, N = NQT
+    const uint32_t idesc = (args.idesc & ~((0x3Fu << 17) | (0x1Fu << 24))) | (uint32_t(NQT >> 3) << 17) | (uint32_t(SBM >> 4) << 24);
+
+    if (warp == kProducerWarp && lane == 0) {
+        prefetch_tmap(&map_q);
+        prefetch_tmap(&map_db);
+        for (int i = 0; i < nstages; ++i) {
+            mbar_init(&bars->full[i], 1);
+            mbar_init(&bars->empty[i], 1);
+        }
+        for (int i = 0; i < kStreamAcc; ++i) {
+            mbar_init(&bars->acc_full[i], 1);
+            mbar_init(&bars->acc_empty[i], 4);
+        }
+        mbar_init(&bars->queries, 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc<1>(&bars->tmem_base, kStreamTmemCols);
+    if (threadIdx.x < 64) thr_s[threadIdx.x] = (threadIdx.x < NQT && threadIdx.x < args.nq) ? args.thr[threadIdx.x] : FLT_MAX;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == kProducerWarp) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars->queries, uint32_t(args.num_kb) * bytes_q_kb);
+            for (int kb = 0; kb < args.num_kb; ++kb)
+                tma_load_2d(smem_q + size_t(kb) * bytes_q_kb, &map_q, &bars->queries, kb * BK, 0, args.hint_q);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int row_db = int(args.j0) + tile * SBM;
+                for (int kb = 0; kb < args.num_kb; ++kb) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bars->full[stage], kStreamBytesA);
+                    tma_load_2d(smem_a + size_t(stage) * kStreamBytesA, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            mbar_wait(&bars->queries, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * NQT);
+                for (int kb = 0; kb < args.num_kb; ++kb) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(smem_a + size_t(stage) * kStreamBytesA));
+                    const uint64_t db = make_smem_desc(smem_u32(smem_q + size_t(kb) * bytes_q_kb));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16<1>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit<1>(&bars->empty[stage]);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit<1>(&bars->acc_full[acc]);
+                if (++acc == kStreamAcc) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: warp w owns database rows 32 w .. 32 w + 31 of the tile (TMEM lanes) =====
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int nq = int(args.nq < NQT ? args.nq : NQT);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int64_t j = args.j0 + int64_t(tile) * SBM + warp * 32 + lane;  // this thread's database row
+            const bool row_ok = j < args.j1;
+            float yn = 0.f;
+            if (L2 && row_ok) yn = __ldg(args.ynorm2 + j);
+            mbar_wait(&bars->acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + uint32_t(acc * NQT) + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NQT; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + uint32_t(c0), r);
+                tmem_ld_wait();
+                if (c0 < nq && row_ok) {
+                    if (DENSE) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (c0 + i < nq) {  // lanes of a warp hold consecutive rows: coalesced per query
+                                float v = __uint_as_float(r[i]);
+                                if (L2) v = 2.0f * v - yn;
+                                args.cand_scores[int64_t(c0 + i) * args.cap + (j - args.j0)] = v;
+                                args.cand_ids[int64_t(c0 + i) * args.cap + (j - args.j0)] = uint32_t(j);
+                            }
+                        }
+                    } else {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float v = __uint_as_float(r[i]);
+                            if (L2) v = 2.0f * v - yn;
+                            r[i] = __float_as_uint(v);
+                            mask |= (v >= thr_s[c0 + i]) ? (1u << i) : 0u;  // padding queries carry +FLT_MAX
+                        }
+                        while (mask) {  // rare once the thresholds have tightened
+                            const int i = __ffs(int(mask)) - 1;
+                            mask &= mask - 1;
+                            float v = 0.f;
+#pragma unroll
+                            for (int u = 0; u < 32; ++u) v = (u == i) ? __uint_as_float(r[u]) : v;  // no dynamic register indexing
+                            const int64_t q = c0 + i;
+                            const int pos = atomicAdd(args.counts + q, 1);
+                            if (pos < args.cap) {
+                                args.cand_scores[q * int64_t(args.cap) + pos] = v;
+                                args.cand_ids[q * int64_t(args.cap) + pos] = uint32_t(j);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();  // reconverge before the next warp-wide tcgen05.ld
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+            if (++acc == kStreamAcc) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, kStreamTmemCols);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -553,12 +732,14 @@ struct GemmPlan {
     int l2_hints = 0;   // 1: queries evict-last, database evict-first
     int debug_skip_epilogue = 0;
     int stages = 0;     // 0: default depth (4)
+    int stream_kernel = 1;  // launches with <= 64 queries use the few-queries variant (database rows as the M operand)
 };
 
 void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
 void gemm_plan_set_l2_hints(GemmPlan* p, int on) { p->l2_hints = on; }
 void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue) { p->debug_skip_epilogue = skip_epilogue; }
 void gemm_plan_set_stages(GemmPlan* p, int stages) { p->stages = stages; }
+void gemm_plan_set_stream_kernel(GemmPlan* p, int on) { p->stream_kernel = on; }
 int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
@@ -634,6 +815,70 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     return KNN_OK;
 }
 
+template <int NQT, bool L2, bool DENSE>
+static int launch_stream_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorMap& map_db, const GemmArgs& a, size_t smem,
+                                 cudaStream_t s) {
+    auto kern = gemm_stream_kernel<NQT, L2, DENSE>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    KNN_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const int grid = a.n_tiles < p->sms ? a.n_tiles : p->sms;
+    kern<<<grid, kThreads, smem, s>>>(map_q, map_db, a);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+// Few-queries launch: returns KNN_OK and sets *done when the stream kernel took the launch.
+static int try_stream_launch(GemmPlan* p, const h16_t* xq_h16, int fmt, int64_t nq, int64_t nq_pad, int dp, const h16_t* xb_h16,
+                             int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1, int metric, bool dense_first,
+                             FilterState st, cudaStream_t s, bool* done) {
+    *done = false;
+    if (!p->stream_kernel || nq > 64 || nq_pad < 64 || dp % BK != 0) return KNN_OK;
+    const int nqt = nq <= 32 ? 32 : 64;
+    const int num_kb = dp / BK;
+    int stages = kStreamMaxStages;
+    while (stages >= 4 && stream_smem_bytes(nqt, num_kb, stages) > size_t(227 * 1024)) --stages;
+    if (stages < 4) return KNN_OK;  // the resident queries leave no room for a ring: the main kernel takes it
+    CUtensorMap map_q, map_db;
+    KNN_CHECK(make_map(p, &map_q, xq_h16, nq_pad, dp, nqt));
+    KNN_CHECK(make_map(p, &map_db, xb_h16, ntotal, dp, SBM));
+    GemmArgs a;
+    a.nq = nq;
+    a.m_tiles = 1;
+    a.n_tiles = int((j1 - j0 + SBM - 1) / SBM);
+    a.num_kb = num_kb;
+    a.j0 = j0;
+    a.j1 = j1;
+    a.ynorm2 = ynorm2;
+    a.thr = st.thr;
+    a.counts = st.counts;
+    a.cand_scores = st.cand_scores;
+    a.cand_ids = st.cand_ids;
+    a.cap = st.cap;
+    a.debug_skip_epilogue = 0;
+    a.idesc = Cfg<1>::instr_desc(fmt, fmt);
+    a.stages = stages;
+    a.hint_q = kEvictNormal;
+    a.hint_db = kEvictNormal;
+    const size_t smem = stream_smem_bytes(nqt, num_kb, stages);
+    const bool l2 = metric == KNN_METRIC_L2;
+    *done = true;
+#define KNN_STREAM_DISPATCH(NQTV)                                                                                     \
+    if (l2) {                                                                                                          \
+        return dense_first ? launch_stream_variant<NQTV, true, true>(p, map_q, map_db, a, smem, s)                     \
+                           : launch_stream_variant<NQTV, true, false>(p, map_q, map_db, a, smem, s);                   \
+    } else {                                                                                                           \
+        return dense_first ? launch_stream_variant<NQTV, false, true>(p, map_q, map_db, a, smem, s)                    \
+                           : launch_stream_variant<NQTV, false, false>(p, map_q, map_db, a, smem, s);                  \
+    }
+    if (nqt == 32) { KNN_STREAM_DISPATCH(32) } else { KNN_STREAM_DISPATCH(64) }
+#undef KNN_STREAM_DISPATCH
+}
+
 int gemm_filter_launch(GemmPlan* p, const h16_t* xq_h16, int fmt_q, int64_t nq, int64_t nq_pad, int dp,
                        const h16_t* xb_h16, int fmt_db, int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1,
                        int metric, bool dense_first, FilterState st, cudaStream_t s) {
@@ -646,6 +891,11 @@ int gemm_filter_launch(GemmPlan* p, const h16_t* xq_h16, int fmt_q, int64_t nq, 
     if (dense_first && j1 - j0 > st.cap) {
         set_error("gemm_filter: dense panel larger than the candidate capacity");
         return KNN_ERR_INVALID;
+    }
+    if (fmt_q == fmt_db) {
+        bool done = false;
+        KNN_CHECK(try_stream_launch(p, xq_h16, fmt_q, nq, nq_pad, dp, xb_h16, ntotal, ynorm2, j0, j1, metric, dense_first, st, s, &done));
+        if (done) return KNN_OK;
     }
     CUtensorMap map_q, map_db;
     KNN_CHECK(make_map(p, &map_q, xq_h16, nq_pad, dp, BM));

@@ -117,6 +117,7 @@ struct knn_index {
     int l2_hints = 0;
     int debug_skip_epilogue = 0;
     int gemm_stages = 0;
+    int stream_kernel = 1;
     int panel_ratio = 0;  // 0: automatic
     int64_t small_batch_nq = 256;  // batches up to this size use growth ratio 8
     int shadow_param = 0;          // 16-bit format of the tensor-core operands: 0 automatic (desired_shadow), 1 bf16, 2 fp16
@@ -354,6 +355,7 @@ int tensor_prepare(knn_index* ix) {
     gemm_plan_set_l2_hints(ix->plan, ix->l2_hints);
     gemm_plan_set_debug(ix->plan, ix->debug_skip_epilogue);
     gemm_plan_set_stages(ix->plan, ix->gemm_stages);
+    gemm_plan_set_stream_kernel(ix->plan, ix->stream_kernel);
     return KNN_OK;
 }
 
@@ -908,6 +910,7 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "cta_group" && (value == 1 || value == 2)) ix->cta_group = int(value);
     else if (n == "l2_hints") ix->l2_hints = value != 0;
     else if (n == "gemm_stages" && value >= 0 && value <= 6) ix->gemm_stages = int(value);
+    else if (n == "stream_kernel") ix->stream_kernel = value != 0;
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
     else if (n == "small_batch_nq" && value >= 0) ix->small_batch_nq = value;
     else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);

@@ -155,13 +155,26 @@ __device__ int block_select_sorted(const Gen& gen, int L, int k, SelectSmem& sm)
             int need, bucket_count;
             radix_narrow<uint64_t>(gen, L, k, kSortCap, mn, mx, sm.hist, &sm.bucket, &sm.cum_gt, &sm.bucket_count,
                                    prefix, mask, need, bucket_count);
+            // First every key strictly above the boundary bucket (fewer than k <= kSortCap / 2 of them: none may be
+            // lost), then the bucket's keys while there is room.  The bucket only exceeds the room when the narrowing
+            // ran out of bits, i.e. its keys are identical - padding (valid keys are distinct) - so dropping some is
+            // harmless; taking bucket keys in the same pass could crowd out real keys, e.g. a rescored list in which
+            // fewer than k entries are still valid and thousands are padding.
             if (tid == 0) sm.scount = 0;
             __syncthreads();
             for (int i = tid; i < L; i += T) {
                 const uint64_t key = gen(i);
-                if ((key & mask) >= prefix) {
+                if ((key & mask) > prefix) {
                     const int p = atomicAdd(&sm.scount, 1);
-                    if (p < kSortCap) sm.keys[p] = key;  // overflow only for a bucket of identical padding keys
+                    if (p < kSortCap) sm.keys[p] = key;  // always true: fewer than k keys lie above the bucket
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < L; i += T) {
+                const uint64_t key = gen(i);
+                if ((key & mask) == prefix) {
+                    const int p = atomicAdd(&sm.scount, 1);
+                    if (p < kSortCap) sm.keys[p] = key;
                 }
             }
             __syncthreads();

@@ -365,6 +365,24 @@ def test_bf16_storage_index(knn):
         check_parity(D, I, D_ref, I_ref, xq, xb_r, IP, max_excused_frac=2e-3)
 
 
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("nq,nb,d,k", [(1, 20000, 1024, 100), (17, 9000, 96, 10), (32, 30000, 256, 1000), (33, 12345, 1024, 5),
+                                       (64, 50000, 512, 200), (5, 8192, 1900, 13), (40, 8192, 1900, 13), (64, 70000, 64, 2048)])
+def test_few_queries_stream_kernel(knn, nq, nb, d, k, metric):
+    """Launches with <= 64 queries take the few-queries variant of the GEMM kernel (database rows as the M operand,
+    queries resident in shared memory) unless the resident queries leave no room for the ring (d = 1900, nq > 32).
+    Same bits as the main kernel and as the exact scan, both operand formats, dense first panel included."""
+    xq, xb = _data(nq, nb, d, seed=nq * 7 + d, normalize=metric == IP, scale=1.3)
+    D1, I1, _ = _search(knn, xq, xb, k, metric, path=1)
+    for fmt in (BF16, FP16):
+        for stream in (1, 0):
+            D, I, idx = _search(knn, xq, xb, k, metric, path=2, shadow_fmt=fmt, stream_kernel=stream)
+            assert idx.stat("path") == 2 and idx.stat("overflow_batches") == 0
+            assert np.array_equal(I, I1) and np.array_equal(D, D1), (fmt, stream)
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    check_parity(D1, I1, D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-3 if metric == IP else 1e-2)
+
+
 def test_shadow_format_is_chosen_from_the_data(knn):
     """fp16 shadow rows while the data sits inside fp16's range (3 more mantissa bits than bf16 -> smaller error
     bound -> fewer candidates to rescore); data outside it (saturating or flushing to zero) is noticed through the
@@ -494,6 +512,28 @@ def keep_inverse(I, keep):
     inv = np.full(int(keep.max()) + 1, -1, dtype=np.int64)
     inv[keep] = np.arange(len(keep))
     return inv[I]
+
+
+def test_select_keeps_every_real_entry_among_thousands_of_padding(knn):
+    """Found by tests/test_gpu_fuzz.py: when a list longer than the in-shared-memory sort capacity (4096) holds
+    FEWER than k real entries and thousands of padding ones (a shard's rescored list after the cross-shard bound has
+    been applied, k = 2000), the padding must not crowd real entries out of the sort buffer."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    nl, nq, k, real = 3, 50, 2000, 300
+    D = torch.full((nl, nq, k), -np.finfo(np.float32).max, device="cuda")
+    I = torch.full((nl, nq, k), -1, dtype=torch.int64, device="cuda")
+    vals = torch.stack([(torch.randperm(1 << 20, device="cuda", generator=g)[:nl * real] + 1).float() / (1 << 20) for _ in range(nq)])
+    D[:, :, :real] = torch.sort(vals.view(nq, nl, real).permute(1, 0, 2), dim=2, descending=True)[0]  # distinct scores: no ties
+    I[:, :, :real] = torch.stack([torch.randperm(100000, device="cuda", generator=g)[:nl * real].view(nl, real) for _ in range(nq)], dim=1)
+    Dm, Im = knn.merge_topk(D, I, IP)
+    flatD = D[:, :, :real].permute(1, 0, 2).reshape(nq, nl * real)
+    flatI = I[:, :, :real].permute(1, 0, 2).reshape(nq, nl * real)
+    order = torch.argsort(flatD, dim=1, descending=True, stable=True)
+    assert torch.equal(Dm[:, :nl * real], torch.gather(flatD, 1, order))
+    assert torch.equal(Im[:, :nl * real], torch.gather(flatI, 1, order))
+    assert (Im[:, nl * real:] == -1).all()
 
 
 def test_torch_device_api_and_merge(knn):
