@@ -241,7 +241,8 @@ def main():
             # the raw host-pointer C-ABI call: H2D of the queries, search, D2H of (D, I)
             index.local.search_into(xq_host.data_ptr(), args.nq, args.k, D_host.data_ptr(), I_host.data_ptr())
         else:
-            xq = xq_host.to(dev, non_blocking=True)
+            # every rank holds the host queries: each uploads 1/N of them, one all-gather over NVLink does the rest
+            xq = index.upload_queries(xq_host)
             D, I = index.search(xq, args.k)
             if rank == 0:
                 D_host.copy_(D, non_blocking=True)

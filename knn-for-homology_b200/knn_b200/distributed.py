@@ -281,6 +281,30 @@ class ShardedIndexFlat:
         seg = torch.bucketize(I.clamp(min=0), starts, right=True) - 1
         return torch.where(I >= 0, I + offs[seg], I)
 
+    def upload_queries(self, x_host):
+        """Host queries that EVERY rank holds (the reference's drivers load the same file in every process) -> the full
+        (n, d) float32 matrix on this rank's device, crossing PCIe once in total instead of once per rank: rank r
+        uploads rows [r n/G, (r+1) n/G) and one all-gather over NVLink hands every rank the rest (C4 on 8 GPUs: 51 MB
+        instead of 410 MB over each rank's PCIe link).  x_host: CPU torch tensor (pinned for an asynchronous copy) or
+        numpy array, float32, C-contiguous.  Collective."""
+        import torch
+
+        if isinstance(x_host, np.ndarray):
+            x_host = torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))
+        n, d = x_host.shape
+        dev = torch.device("cuda", self.local.device) if self._dist.is_initialized() and self._dist.get_backend(self.group) == "nccl" \
+            else x_host.device
+        if self.world == 1:
+            return x_host.to(dev, non_blocking=True)
+        chunk = -(-n // self.world)  # equal chunks (all_gather_into_tensor); the tail of the last one is padding
+        buf = torch.empty((self.world * chunk, d), dtype=torch.float32, device=dev)
+        lo, hi = min(n, self.rank * chunk), min(n, (self.rank + 1) * chunk)
+        mine = buf[self.rank * chunk:(self.rank + 1) * chunk]
+        if hi > lo:
+            mine[:hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+        self._dist.all_gather_into_tensor(buf, mine, group=self.group)
+        return buf[:n]
+
     def search(self, x, k: int):
         """Returns the merged (D, I) on every rank (torch tensors on the local index's device, or
         numpy arrays when x is numpy).  Calls with more queries than the two-phase search keeps resident

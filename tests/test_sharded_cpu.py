@@ -74,6 +74,10 @@ def _worker(rank, world, port, metric, weights, out):
         D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
         assert np.array_equal(I, I_ref), (rank, k)
         assert np.array_equal(D, D_ref), (rank, k)
+    # queries every rank holds are uploaded in slices and all-gathered: same matrix on every rank
+    xq_all = index.upload_queries(xq)
+    assert xq_all.shape == xq.shape and np.array_equal(xq_all.numpy(), xq)
+    assert np.array_equal(index.upload_queries(xq[:1]).numpy(), xq[:1])  # fewer rows than ranks
     index.TWO_PHASE_MAX_QUERIES = 5  # more queries than one two-phase call holds: processed in chunks (17 = 5+5+5+2)
     D, I = index.search(xq, 7)
     D_ref, I_ref = fo.knn_flat(xq, xb, 7, metric)
