@@ -8,12 +8,16 @@ Workload (config C4 of BASELINE.json / SURVEY.md section 8d): synthetic 10M x 10
 database of L2-normalised N(0,1) rows (seeded per 65536-row block, so any GPU count builds
 the same database), 100k normalised queries, k = 100, inner product.  One "step" = one full
 pass of index.search over all queries.  With N GPUs the database is row-sharded (strong
-scaling: total work fixed), every rank scores all queries against its shard, results are
-all-gathered over NCCL and merged on the device.
+scaling: total work fixed; shard sizes proportional to each GPU's measured speed unless
+--no-balance), every rank scores all queries against its shard, the shards exchange a per-query
+bound on the k-th best score (one NCCL all-reduce) before the exact rescoring, and the per-shard
+results are exchanged and merged in one kernel over NVLink peer memory.
 
 Legs, all in one JSON line printed by rank 0:
   value     queries/s with the queries already resident in HBM (device-pointer C-ABI call)
-  e2e       same through the host-pointer C-ABI call: pinned host queries -> H2D -> search -> D2H
+  e2e       same from pinned host queries to (D, I) in pinned host memory: N = 1 the host-pointer C-ABI call
+            (H2D -> search -> D2H inside it); N > 1 every rank uploads 1/N of the queries, all-gather, search,
+            rank 0 reads the result back
   roofline  the tcgen05 GEMM kernel: 2*nq*N*d flop / CUDA-event time of its launches
   cpu_baseline  blocked sgemm + top-k on the host cores (bounded sample, scaled by N)
 --impl reference times the CPU implementation only (see oracle/cpu_baseline.py).
