@@ -179,8 +179,9 @@ int knn_prefilter_emit_dev(int64_t nq, int64_t k, const int64_t* I_dev, const fl
  * "cta_group" (tcgen05 cta_group of the GEMM kernel, 1 or 2), "tensor_min_nq", "tensor_min_n",
  * "shadow_fmt" (16-bit format of the tensor-core operands: 0 automatic - fp16 where the exact rescoring
  * dominates and the data fits its range, bf16 where the GEMM does -, 1 bf16, 2 fp16; results never depend on it),
- * "mantissa_bits" (experiments: mantissa bits kept in bf16 operands, 0 = all 7).
- * Statistics of the last search: "path", "launches", "gemm_launches", "gemm_ms", "overflow_batches",
+ * "mantissa_bits" (experiments: mantissa bits kept in bf16 operands, 0 = all 7), "stream_kernel" (1: launches
+ * with <= 64 queries use the few-queries variant of the GEMM kernel; default on), "gemm_stages", "panel_ratio".
+ * Statistics of the last search: "path", "launches", "gemm_launches", "gemm_ms", "rerank_ms", "overflow_batches",
  * "overflow_queries"; of the index: "capacity", "shadow_fmt" (1 bf16, 2 fp16), "mantissa_bits",
  * "shadow_conversions" (times the shadow rows were rewritten in the other format). */
 int knn_index_set_param(knn_index* idx, const char* name, int64_t value);
