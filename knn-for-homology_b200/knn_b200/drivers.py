@@ -28,14 +28,21 @@ def _upload(x: np.ndarray, device: int):
     return torch.from_numpy(x).to(torch.device("cuda", device))
 
 
-def search(embeddings: np.ndarray, hits: int = 10, metric: int = METRIC_INNER_PRODUCT, device: int | None = None):
+def search(embeddings: np.ndarray, hits: int = 10, metric: int = METRIC_INNER_PRODUCT, device: int | None = None,
+           index: IndexFlat | None = None):
     """All-vs-all search; one more hit is searched internally because the first one is the self hit
-    (cath/search.py:16).  The caller's array is not modified (the reference normalises a copy)."""
+    (cath/search.py:16).  The caller's array is not modified (the reference normalises a copy).
+    ``index``: an IndexFlat of the same width and metric to reuse (it is reset first): a loop over many matrices
+    then pays for the device storage and the ~1 GB of search workspaces once instead of once per matrix."""
     device = _default_device() if device is None else device
     x = _upload(embeddings, device)
     if metric == METRIC_INNER_PRODUCT:
         normalize_L2(x)
-    index = IndexFlat(x.shape[1], metric, device=device)
+    if index is None:
+        index = IndexFlat(x.shape[1], metric, device=device)
+    else:
+        assert (index.d, index.metric_type) == (x.shape[1], metric), "reused index has another width or metric"
+        index.reset()
     index.add(x)
     scores, results = index.search(x, hits + 1)
     scores, results = scores.cpu().numpy(), results.cpu().numpy()
@@ -50,12 +57,17 @@ def search_and_save(cath_data: Path, device: int | None = None) -> None:
     for name, metric in [("Cosine", METRIC_INNER_PRODUCT), ("Euclidean", METRIC_L2)]:
         print(f"Searching with {name}")
         hits, scores = {}, {}
+        indexes = {}  # one index per embedding width, reused across the files (the embedders differ in width)
         for file_path in sorted(cath_data.glob("*.npy")):
             # fp16 embeddings of the half precision model are cast to the fp32 the index wants (cath/search.py:39-40)
             embeddings = np.load(file_path).astype(np.float32)
             print(file_path.stem, embeddings.shape)
             start = time.time()
-            hits[file_path.stem], scores[file_path.stem] = search(embeddings, metric=metric, device=device)
+            if embeddings.shape[1] not in indexes:
+                indexes[embeddings.shape[1]] = IndexFlat(embeddings.shape[1], metric,
+                                                         device=_default_device() if device is None else device)
+            hits[file_path.stem], scores[file_path.stem] = search(embeddings, metric=metric, device=device,
+                                                                  index=indexes[embeddings.shape[1]])
             end = time.time()
             print(end - start)
             cath_data.joinpath(file_path.with_suffix(f".{name.lower()}-search-time.txt")).write_text(str(end - start))
