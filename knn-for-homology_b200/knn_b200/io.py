@@ -25,7 +25,11 @@ _HEADER = struct.Struct("<4siqqqBi")
 
 
 def write_index(index: IndexFlat, path: str) -> None:
-    if not isinstance(index, IndexFlat):
+    """Any flat index works that has ``d``, ``ntotal``, ``metric_type`` and ``reconstruct_n(i0, n)`` (the CPU test of
+    the byte layout passes a host-side stand-in; the product passes an IndexFlat)."""
+    if not all(hasattr(index, a) for a in ("d", "ntotal", "metric_type", "reconstruct_n")):
+        raise TypeError("write_index: only flat indexes are supported")
+    if index.metric_type not in (METRIC_INNER_PRODUCT, METRIC_L2):
         raise TypeError("write_index: only flat indexes are supported")
     fourcc = b"IxFI" if index.metric_type == METRIC_INNER_PRODUCT else b"IxF2"
     n = index.ntotal
@@ -34,10 +38,11 @@ def write_index(index: IndexFlat, path: str) -> None:
         f.write(struct.pack("<Q", n * index.d))
         step = max(1, (64 << 20) // (4 * index.d))
         for i0 in range(0, n, step):
-            index.reconstruct_n(i0, min(step, n - i0)).tofile(f)
+            np.ascontiguousarray(index.reconstruct_n(i0, min(step, n - i0)), dtype="<f4").tofile(f)
 
 
-def read_index(path: str, device: int | None = None) -> IndexFlat:
+def read_index(path: str, device: int | None = None, index_factory=None) -> IndexFlat:
+    """``index_factory(d, metric)``: what to build instead of a device IndexFlat (CPU tests of the byte layout)."""
     with open(path, "rb") as f:
         head = f.read(_HEADER.size)
         if len(head) != _HEADER.size:
@@ -50,8 +55,11 @@ def read_index(path: str, device: int | None = None) -> IndexFlat:
         (count,) = struct.unpack("<Q", f.read(8))
         if count != n * d:
             raise ValueError("read_index: vector count %d != ntotal*d %d" % (count, n * d))
-        index = IndexFlat(d, metric, device=device)
-        index.reserve(n)
+        if index_factory is None:
+            index = IndexFlat(d, metric, device=device)
+            index.reserve(n)
+        else:
+            index = index_factory(d, metric)
         step = max(1, (64 << 20) // (4 * d))
         for i0 in range(0, n, step):
             m = min(step, n - i0)

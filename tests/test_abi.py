@@ -89,3 +89,43 @@ def test_product_never_imports_the_oracle():
         if p.suffix in {".py", ".cu", ".cuh", ".h"}:
             assert "oracle" not in p.read_text().replace("see oracle/flat_oracle.py", "").replace(
                 "oracle/flat_oracle.py", ""), p
+
+
+def test_flat_index_file_byte_layout(tmp_path):
+    """write_index / read_index on a host-side stand-in: the bytes of a faiss 1.7.x flat index file, field by
+    field (fourcc, d, ntotal, two dummies of 1 << 20, is_trained, metric, vector count, float32 rows).  The
+    layout is restated from upstream knowledge (no faiss in this image); this pins it against accidental change."""
+    import struct
+
+    import numpy as np
+
+    from knn_b200 import io as kio
+
+    class HostFlat:
+        def __init__(self, d, metric):
+            self.d, self.metric_type, self.rows = d, metric, np.empty((0, d), np.float32)
+
+        ntotal = property(lambda self: self.rows.shape[0])
+
+        def reconstruct_n(self, i0, n):
+            return self.rows[i0:i0 + n]
+
+        def add(self, x):
+            self.rows = np.concatenate([self.rows, x])
+
+    for metric, fourcc in [(0, b"IxFI"), (1, b"IxF2")]:
+        src = HostFlat(3, metric)
+        src.add(np.arange(6, dtype=np.float32).reshape(2, 3) / 4)
+        path = tmp_path / f"m{metric}.index"
+        kio.write_index(src, str(path))
+        raw = path.read_bytes()
+        want = (fourcc + struct.pack("<i", 3) + struct.pack("<q", 2) + struct.pack("<qq", 1 << 20, 1 << 20) + b"\x01"
+                + struct.pack("<i", metric) + struct.pack("<Q", 6) + (np.arange(6, dtype="<f4") / 4).tobytes())
+        assert raw == want and len(raw) == 4 + 4 + 8 + 16 + 1 + 4 + 8 + 24
+        back = kio.read_index(str(path), index_factory=HostFlat)
+        assert (back.d, back.ntotal, back.metric_type) == (3, 2, metric) and np.array_equal(back.rows, src.rows)
+    (tmp_path / "bad").write_bytes(b"IxHN" + b"\0" * 60)
+    with pytest.raises(NotImplementedError):
+        kio.read_index(str(tmp_path / "bad"), index_factory=HostFlat)
+    with pytest.raises(TypeError):
+        kio.write_index(object(), str(tmp_path / "x"))
