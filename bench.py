@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-phases", action="store_true", help="skip the extra untimed pass that times the phases of the sharded search")
     ap.add_argument("--bf16-storage", action="store_true", help="the bf16 values ARE the database (config C5): no fp32 master rows")
     ap.add_argument("--shadow-fmt", type=int, default=0, choices=[0, 1, 2], help="16-bit format of the tensor-core copy of the database: 0 automatic, 1 bf16, 2 fp16")
+    ap.add_argument("--query-groups", type=int, default=1, help="N > 1: rows x query-groups grid of ranks (GridIndexFlat; not the default: "
+                    "host logic tested under gloo, not yet timed on GPUs)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: equal row shards instead of shards proportional to each GPU's measured speed")
     ap.add_argument("--mantissa-bits", type=int, default=0, help="mantissa bits kept in bf16 tensor-core operands: 0 automatic, 2..7")
     return ap.parse_args()
@@ -165,7 +167,8 @@ def workload_config(args, world):
     return {"workload": f"{name}: synthetic normalised {args.nb}x{D_DIM} {store} database, {args.nq} queries, k={args.k}, "
                         f"inner product, exact (ids = fp32 IndexFlatIP on the stored values)",
             "database_rows": args.nb, "queries_per_step": args.nq, "k": args.k, "d": D_DIM,
-            "sharding": f"rows over {world} GPU(s)", "l2": "inputs larger than L2 (bf16 database shard >> 126 MB)"}
+            "sharding": (f"rows over {world} GPU(s)" if getattr(args, "query_groups", 1) <= 1 or world == 1 else
+                         f"{args.query_groups} query groups x rows over {world // args.query_groups} GPU(s)"), "l2": "inputs larger than L2 (bf16 database shard >> 126 MB)"}
 
 
 def main():
@@ -182,7 +185,7 @@ def main():
     import torch.distributed as dist
 
     import knn_b200
-    from knn_b200.distributed import ShardedIndexFlat, measured_rank_speeds, shard_bounds
+    from knn_b200.distributed import GridIndexFlat, ShardedIndexFlat, measured_rank_speeds, shard_bounds
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -197,10 +200,18 @@ def main():
     if world > 1 and not args.no_balance:
         weights = measured_rank_speeds(D_DIM, local_rank, seconds=2.0)
     t_build = time.perf_counter()
-    index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank, bf16_storage=args.bf16_storage,
-                             shard_weights=weights)
-    b = shard_bounds(args.nb, world, weights)
-    lo, hi = b[rank], b[rank + 1]
+    Q = args.query_groups if world > 1 else 1
+    if Q > 1:  # R = world / Q row shards per query group; every group holds the whole database
+        index = GridIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, query_groups=Q, device=local_rank,
+                              bf16_storage=args.bf16_storage, shard_weights=weights)
+        R = world // Q
+        b = shard_bounds(args.nb, R, weights[(rank // R) * R:(rank // R + 1) * R] if weights else None)
+        lo, hi = b[rank % R], b[rank % R + 1]
+    else:
+        index = ShardedIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, device=local_rank, bf16_storage=args.bf16_storage,
+                                 shard_weights=weights)
+        b = shard_bounds(args.nb, world, weights)
+        lo, hi = b[rank], b[rank + 1]
     index.local.set_param("cta_group", args.cta_group)
     if args.shadow_fmt and not args.bf16_storage:
         index.local.set_param("shadow_fmt", args.shadow_fmt)
@@ -246,7 +257,7 @@ def main():
             index.local.search_into(xq_host.data_ptr(), args.nq, args.k, D_host.data_ptr(), I_host.data_ptr())
         else:
             # every rank holds the host queries: each uploads 1/N of them, one all-gather over NVLink does the rest
-            xq = index.upload_queries(xq_host)
+            xq = index.upload_queries(xq_host) if Q == 1 else xq_host.to(dev, non_blocking=True)
             D, I = index.search(xq, args.k)
             if rank == 0:
                 D_host.copy_(D, non_blocking=True)
@@ -320,7 +331,7 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         n_shard = hi - lo
-        flops_per_step = 2.0 * args.nq * n_shard * D_DIM
+        flops_per_step = 2.0 * (args.nq / Q) * n_shard * D_DIM  # this rank's GEMM work: its rows x its query group's queries
         achieved = flops_per_step * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         peak = peaks["tflops_sustained"]
         traffic, traffic_note = ncu_traffic()
@@ -347,7 +358,7 @@ def main():
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
             "search_path": search_path, "cta_group": args.cta_group, "phases_ms_rank0": phases, "ms_per_step_by_rank": by_rank_value or None,
-            "shard_rows_by_rank": [b[r + 1] - b[r] for r in range(world)],
+            "shard_rows_by_rank": [b[r + 1] - b[r] for r in range(len(b) - 1)], "query_groups": Q,
             "rank_speed_weights": [round(w, 4) for w in weights] if weights else None,
         }
         print(json.dumps(line), flush=True)

@@ -310,6 +310,12 @@ class ShardedIndexFlat:
         numpy arrays when x is numpy).  Calls with more queries than the two-phase search keeps resident
         (TWO_PHASE_MAX_QUERIES) are processed in chunks of that size (config C5: 1M queries)."""
         n = x.shape[0]
+        if n == 0:  # nothing to search (every rank of the group sees the same empty call: no collective is entered)
+            if isinstance(x, np.ndarray):
+                return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
+            import torch
+
+            return (torch.empty((0, k), dtype=torch.float32, device=x.device), torch.empty((0, k), dtype=torch.int64, device=x.device))
         if n > self.TWO_PHASE_MAX_QUERIES and self.world > 1:
             step = self.TWO_PHASE_MAX_QUERIES
             parts, acc = [], {"gemm_ms": 0.0, "gemm_launches": 0.0}
@@ -410,3 +416,91 @@ class ShardedIndexFlat:
                                                        tD, tI, tDo, tIo, _torch_stream(D.device.index)))
         ex.barrier()  # every rank's slice has landed in this rank's buffer
         return D_out.clone(), I_out.clone()
+
+
+class GridIndexFlat:
+    """Rows x query-groups grid of ranks (world = R x Q, rank = g * R + r).
+
+    Row sharding replicates the per-QUERY work of a search (query preparation, threshold tightening after every panel,
+    the finish phase) on every rank: at 8 GPUs that is ~14 ms of a 196 ms C4 step.  Here the Q
+    query groups each hold the WHOLE database, row-sharded over their R ranks (a ShardedIndexFlat on a sub-group), and
+    take 1/Q of the queries of a call; the ranks with the same row position then all-gather their result slices, so
+    every rank still returns the full (D, I).  Per-rank GEMM work is unchanged (Q x more rows, Q x fewer queries than
+    with plain row sharding), the per-query work drops by Q, the database costs Q x the memory (C4: 2 x 15 GB per rank).
+
+    Status: the host logic is covered by a world-size-4 gloo test (tests/test_sharded_cpu.py); it has NOT been timed on
+    GPUs yet (opt-in: bench.py --query-groups Q)."""
+
+    def __init__(self, d: int, metric: int, query_groups: int, device=None, shard_weights=None, **kw):
+        import torch.distributed as dist
+
+        self._dist = dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if query_groups < 1 or world % query_groups:
+            raise ValueError("query_groups must divide the world size")
+        self.Q, self.R = int(query_groups), world // int(query_groups)
+        self.g, self.r = rank // self.R, rank % self.R
+        # every rank creates every sub-group, in the same order (torch.distributed requirement)
+        row_groups = [dist.new_group([g * self.R + r for r in range(self.R)]) for g in range(self.Q)]
+        col_groups = [dist.new_group([g * self.R + r for g in range(self.Q)]) for r in range(self.R)]
+        self.col_group = col_groups[self.r]
+        if shard_weights is not None:  # one weight per rank of the world: this group's slice
+            shard_weights = list(shard_weights)[self.g * self.R:(self.g + 1) * self.R]
+        self.inner = ShardedIndexFlat(d, metric, group=row_groups[self.g], device=device, shard_weights=shard_weights, **kw)
+        self.d, self.metric_type, self.is_trained = self.inner.d, self.inner.metric_type, True
+
+    local = property(lambda self: self.inner.local)
+    ntotal = property(lambda self: self.inner.ntotal)
+    last_stats = property(lambda self: self.inner.last_stats)
+    last_phases_ms = property(lambda self: self.inner.last_phases_ms)
+
+    @property
+    def profile_phases(self):
+        return self.inner.profile_phases
+
+    @profile_phases.setter
+    def profile_phases(self, on):
+        self.inner.profile_phases = on
+
+    def train(self, x) -> None:
+        pass
+
+    def add(self, x) -> None:
+        self.inner.add(x)
+
+    def add_local(self, x_local, global_start: int, n_global: int) -> None:
+        self.inner.add_local(x_local, global_start, n_global)
+
+    def adopt_local(self, global_start: int, n_global: int) -> None:
+        self.inner.adopt_local(global_start, n_global)
+
+    def query_slice(self, n: int):
+        b = shard_bounds(n, self.Q)
+        return b[self.g], b[self.g + 1]
+
+    def search(self, x, k: int):
+        """Every rank passes ALL queries and gets the full (D, I); its group searches rows [lo, hi) of them."""
+        import torch
+
+        as_numpy = isinstance(x, np.ndarray)
+        n = x.shape[0]
+        lo, hi = self.query_slice(n)
+        D, I = self.inner.search(x[lo:hi], k)
+        if self.Q == 1:
+            return D, I
+        if as_numpy:
+            D, I = torch.from_numpy(D), torch.from_numpy(I)
+        chunk = -(-n // self.Q)  # equal chunks for all_gather_into_tensor; the tail of a short slice is padding
+        bufD = torch.empty((self.Q * chunk, k), dtype=D.dtype, device=D.device)
+        bufI = torch.empty((self.Q * chunk, k), dtype=I.dtype, device=I.device)
+        mineD, mineI = bufD[self.g * chunk:(self.g + 1) * chunk], bufI[self.g * chunk:(self.g + 1) * chunk]
+        mineD[:hi - lo].copy_(D)
+        mineI[:hi - lo].copy_(I)
+        self._dist.all_gather_into_tensor(bufD, mineD, group=self.col_group)
+        self._dist.all_gather_into_tensor(bufI, mineI, group=self.col_group)
+        b = shard_bounds(n, self.Q)
+        D = torch.cat([bufD[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
+        I = torch.cat([bufI[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
+        if as_numpy:
+            return D.numpy(), I.numpy()
+        return D, I

@@ -123,3 +123,44 @@ def test_weighted_shard_bounds():
     for bad in ([1, 1], [1, 0, 1, 1]):
         with pytest.raises(ValueError):
             shard_bounds(10, 4, bad)
+
+
+def _grid_worker(rank, world, port, out):
+    sys.path.insert(0, str(REPO))
+    sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from knn_b200.distributed import GridIndexFlat
+    from oracle import flat_oracle as fo
+
+    rng = np.random.default_rng(1)
+    xb = rng.standard_normal((803, 24)).astype(np.float32)
+    xq = rng.standard_normal((21, 24)).astype(np.float32)
+    for metric in (0, 1):
+        # 2 query groups x 2 row shards; unequal shards inside the groups
+        index = GridIndexFlat(24, metric, query_groups=2, index_factory=lambda: _OracleShard(24, metric), merge_fn=_merge_numpy,
+                              shard_weights=[1.0, 1.5, 0.8, 1.2])
+        index.add(xb[:400])
+        index.add(xb[400:])
+        assert index.ntotal == 803 and (index.R, index.Q) == (2, 2)
+        assert index.query_slice(21) == ((0, 10) if rank < 2 else (10, 21))
+        for k in (7, 900):
+            D, I = index.search(xq, k)
+            D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+            assert D.shape == (21, k) and np.array_equal(I, I_ref), (rank, metric, k)
+            assert np.allclose(D, D_ref, rtol=1e-6, atol=1e-6)  # the oracle's sgemm rounds differently per batch shape
+        D, I = index.search(xq[:1], 5)  # fewer queries than groups: one group searches nothing
+        assert np.array_equal(I, fo.knn_flat(xq[:1], xb, 5, metric)[1])
+    if rank == 0:
+        Path(out).write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_grid_index_world4_gloo(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = tmp_path / "ok"
+    mp.spawn(_grid_worker, args=(4, port, str(out)), nprocs=4, join=True)
+    assert out.read_text() == "ok"
