@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--bf16-storage", action="store_true", help="the bf16 values ARE the database (config C5): no fp32 master rows")
     ap.add_argument("--shadow-fmt", type=int, default=0, choices=[0, 1, 2], help="16-bit format of the tensor-core copy of the database: 0 automatic, 1 bf16, 2 fp16")
     ap.add_argument("--query-groups", type=int, default=1, help="N > 1: rows x query-groups grid of ranks (GridIndexFlat; not the default: "
-                    "host logic tested under gloo, not yet timed on GPUs)")
+                    "measured on 2 GPUs only, the 8-GPU shape 2 x 4 is unmeasured)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: equal row shards instead of shards proportional to each GPU's measured speed")
     ap.add_argument("--mantissa-bits", type=int, default=0, help="mantissa bits kept in bf16 tensor-core operands: 0 automatic, 2..7")
     return ap.parse_args()

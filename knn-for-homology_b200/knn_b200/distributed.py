@@ -428,8 +428,9 @@ class GridIndexFlat:
     every rank still returns the full (D, I).  Per-rank GEMM work is unchanged (Q x more rows, Q x fewer queries than
     with plain row sharding), the per-query work drops by Q, the database costs Q x the memory (C4: 2 x 15 GB per rank).
 
-    Status: the host logic is covered by a world-size-4 gloo test (tests/test_sharded_cpu.py); it has NOT been timed on
-    GPUs yet (opt-in: bench.py --query-groups Q)."""
+    Status: the host logic is covered by a world-size-4 gloo test (tests/test_sharded_cpu.py); on GPUs it has run as
+    2 groups x 1 shard (profiles/r01_bench_c4_2gpu_query_groups2.json), the 2 x 4 shape it is meant for is unmeasured
+    (opt-in: bench.py --query-groups Q)."""
 
     def __init__(self, d: int, metric: int, query_groups: int, device=None, shard_weights=None, **kw):
         import torch.distributed as dist
