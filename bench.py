@@ -331,7 +331,11 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         n_shard = hi - lo
-        flops_per_step = 2.0 * (args.nq / Q) * n_shard * D_DIM  # this rank's GEMM work: its rows x its query group's queries
+        nq_rank = args.nq
+        if Q > 1:
+            q_lo, q_hi = index.query_slice(args.nq)
+            nq_rank = q_hi - q_lo
+        flops_per_step = 2.0 * nq_rank * n_shard * D_DIM  # this rank's GEMM work: its rows x its query group's queries
         achieved = flops_per_step * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         peak = peaks["tflops_sustained"]
         traffic, traffic_note = ncu_traffic()

@@ -445,8 +445,12 @@ class GridIndexFlat:
         row_groups = [dist.new_group([g * self.R + r for r in range(self.R)]) for g in range(self.Q)]
         col_groups = [dist.new_group([g * self.R + r for g in range(self.Q)]) for r in range(self.R)]
         self.col_group = col_groups[self.r]
-        if shard_weights is not None:  # one weight per rank of the world: this group's slice
-            shard_weights = list(shard_weights)[self.g * self.R:(self.g + 1) * self.R]
+        self.group_weights = None  # share of the queries every group takes (None: equal shares)
+        if shard_weights is not None:  # one weight per rank of the world
+            w = list(shard_weights)
+            # a group is as fast as its ranks together (its row shards are already sized by their weights)
+            self.group_weights = [sum(w[g * self.R:(g + 1) * self.R]) for g in range(self.Q)]
+            shard_weights = w[self.g * self.R:(self.g + 1) * self.R]
         self.inner = ShardedIndexFlat(d, metric, group=row_groups[self.g], device=device, shard_weights=shard_weights, **kw)
         self.d, self.metric_type, self.is_trained = self.inner.d, self.inner.metric_type, True
 
@@ -475,8 +479,11 @@ class GridIndexFlat:
     def adopt_local(self, global_start: int, n_global: int) -> None:
         self.inner.adopt_local(global_start, n_global)
 
+    def query_bounds(self, n: int):
+        return shard_bounds(n, self.Q, self.group_weights)
+
     def query_slice(self, n: int):
-        b = shard_bounds(n, self.Q)
+        b = self.query_bounds(n)
         return b[self.g], b[self.g + 1]
 
     def search(self, x, k: int):
@@ -491,7 +498,8 @@ class GridIndexFlat:
             return D, I
         if as_numpy:
             D, I = torch.from_numpy(D), torch.from_numpy(I)
-        chunk = -(-n // self.Q)  # equal chunks for all_gather_into_tensor; the tail of a short slice is padding
+        b = self.query_bounds(n)
+        chunk = max(b[g + 1] - b[g] for g in range(self.Q))  # equal chunks for all_gather_into_tensor; tails are padding
         bufD = torch.empty((self.Q * chunk, k), dtype=D.dtype, device=D.device)
         bufI = torch.empty((self.Q * chunk, k), dtype=I.dtype, device=I.device)
         mineD, mineI = bufD[self.g * chunk:(self.g + 1) * chunk], bufI[self.g * chunk:(self.g + 1) * chunk]
@@ -499,7 +507,6 @@ class GridIndexFlat:
         mineI[:hi - lo].copy_(I)
         self._dist.all_gather_into_tensor(bufD, mineD, group=self.col_group)
         self._dist.all_gather_into_tensor(bufI, mineI, group=self.col_group)
-        b = shard_bounds(n, self.Q)
         D = torch.cat([bufD[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
         I = torch.cat([bufI[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
         if as_numpy:
