@@ -133,3 +133,38 @@ def test_parity_checker_rejects_real_mismatch():
     with pytest.raises(ParityError):
         check_parity(D_bad, I, D, I, xq, xb, 0)
     assert check_parity(D, I, D, I, xq, xb, 0)["excused"] == 0
+
+
+def test_parity_checker_excuses_only_fp32_near_ties():
+    """Two rows whose fp64 scores differ by less than tau may swap (both orders are valid fp32 orderings); a duplicate
+    id, an id out of range, a padding mismatch or too many excused positions are rejected."""
+    rng = np.random.default_rng(4)
+    xb = rng.standard_normal((50, 64)).astype(np.float32)
+    xq = rng.standard_normal((3, 64)).astype(np.float32)
+    xb[7] = xb[3]
+    xb[7, 0] = np.nextafter(xb[3, 0], np.float32(10))  # one ulp apart: scores differ far below tau
+    xq[0] = xb[3] * 2
+    D, I = fo.knn_flat(xq, xb, 4, 0)
+    assert set(I[0, :2].tolist()) == {3, 7}
+    I_swapped, D_swapped = I.copy(), D.copy()
+    I_swapped[0, [0, 1]] = I[0, [1, 0]]
+    D_swapped[0, [0, 1]] = D[0, [1, 0]]
+    stats = check_parity(D_swapped, I_swapped, D, I, xq, xb, 0)
+    assert stats["excused"] == 2 and stats["rows_with_ties"] == 1
+    with pytest.raises(ParityError):  # ... but not more of them than the test allows
+        check_parity(D_swapped, I_swapped, D, I, xq, xb, 0, max_excused_frac=0.1)
+    I_dup = I.copy()
+    I_dup[1, 1] = I_dup[1, 0]
+    with pytest.raises(ParityError):
+        check_parity(D, I_dup, D, I, xq, xb, 0)
+    I_oob = I.copy()
+    I_oob[2, 3] = 50
+    with pytest.raises(ParityError):
+        check_parity(D, I_oob, D, I, xq, xb, 0)
+    Dp, Ip = fo.knn_flat(xq, xb[:2], 4, 0)  # k > ntotal: two padded columns
+    I_nopad = Ip.copy()
+    I_nopad[:, 3] = 0
+    with pytest.raises(ParityError):
+        check_parity(Dp, I_nopad, Dp, Ip, xq, xb[:2], 0)
+    with pytest.raises(ParityError):
+        check_parity(D.astype(np.float64), I, D, I, xq, xb, 0)
