@@ -18,9 +18,16 @@ Legs, all in one JSON line printed by rank 0:
   e2e       same from pinned host queries to (D, I) in pinned host memory: N = 1 the host-pointer C-ABI call
             (H2D -> search -> D2H inside it); N > 1 every rank uploads 1/N of the queries, all-gather, search,
             rank 0 reads the result back
+  e2e_pageable  the call the reference's drivers make: pageable numpy queries in, numpy (D, I) out
   roofline  the tcgen05 GEMM kernel: 2*nq*N*d flop / CUDA-event time of its launches
+  parity_vs_fp64  >= 256 sampled queries of the last timed step against an fp64 brute force done with plain torch on
+            every rank's shard (regenerated rows, fp64 matmul, local top-(k+8), all-gather, merge on rank 0 with the
+            lower-id tie rule) - nothing of the engine is on that side.  A mismatch beyond the fp32 tie tolerance or a
+            distance off by more than 1e-5 relative makes the run exit non-zero.
+  small_batch   N = 1: whole index.search calls with 1..256 queries on the resident database against the HBM roofline
   cpu_baseline  blocked sgemm + top-k on the host cores (bounded sample, scaled by N)
 --impl reference times the CPU implementation only (see oracle/cpu_baseline.py).
+--config c2|c3 selects the rescoring-heavy all-vs-all stand-ins of BASELINE.json's configs 2 and 3 (k = 1000).
 """
 import argparse
 import json
@@ -60,7 +67,22 @@ def parse():
                     "measured on 2 GPUs only, the 8-GPU shape 2 x 4 is unmeasured)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: equal row shards instead of shards proportional to each GPU's measured speed")
     ap.add_argument("--mantissa-bits", type=int, default=0, help="mantissa bits kept in bf16 tensor-core operands: 0 automatic, 2..7")
-    return ap.parse_args()
+    ap.add_argument("--config", default="c4", choices=["c4", "c2", "c3", "c5"],
+                    help="c4 (default): 10M x 1024, 100k queries, k=100.  c2: CATH20 stand-in, 14433 all-vs-all, k=1000.  "
+                         "c3: Pfam20 stand-in, 300k all-vs-all, k=1000.  c5: 100M bf16 rows, 1M queries, k=1000 (8 GPUs)")
+    ap.add_argument("--no-small-batch", action="store_true", help="N = 1: skip the small-batch (HBM roofline) legs")
+    ap.add_argument("--no-overlap", action="store_true", help="finish phase of a batch on the main stream (no side stream)")
+    ap.add_argument("--parity-queries", type=int, default=256)
+    args = ap.parse_args()
+    if args.config == "c2":
+        args.nb, args.nq, args.k, args.all_vs_all = 14_433, 14_433, 1000, True
+    elif args.config == "c3":
+        args.nb, args.nq, args.k, args.all_vs_all = 300_000, 300_000, 1000, True
+    elif args.config == "c5":
+        args.nb, args.nq, args.k, args.bf16_storage, args.all_vs_all = 100_000_000, 1_000_000, 1000, True, False
+    else:
+        args.all_vs_all = False
+    return args
 
 
 def measured_peaks():
@@ -163,12 +185,98 @@ def workload_config(args, world):
     name = "C4" if (args.nb, args.nq, args.k) == (10_000_000, 100_000, 100) else "custom"
     if (args.nb, args.nq, args.k, args.bf16_storage) == (100_000_000, 1_000_000, 1000, True):
         name = "C5"
+    if getattr(args, "all_vs_all", False):
+        name = {"c2": "C2 stand-in (CATH20 all-vs-all)", "c3": "C3 stand-in (Pfam20 all-vs-all)"}[args.config]
     store = "bf16" if args.bf16_storage else "fp32"
     return {"workload": f"{name}: synthetic normalised {args.nb}x{D_DIM} {store} database, {args.nq} queries, k={args.k}, "
                         f"inner product, exact (ids = fp32 IndexFlatIP on the stored values)",
             "database_rows": args.nb, "queries_per_step": args.nq, "k": args.k, "d": D_DIM,
             "sharding": (f"rows over {world} GPU(s)" if getattr(args, "query_groups", 1) <= 1 or world == 1 else
                          f"{args.query_groups} query groups x rows over {world // args.query_groups} GPU(s)"), "l2": "inputs larger than L2 (bf16 database shard >> 126 MB)"}
+
+
+def gen_block(blk, nb, dev):
+    """Rows [blk * BLOCK_ROWS, ...) of the synthetic database: seeded per block, so any GPU count builds the same one."""
+    import torch
+
+    import knn_b200
+
+    r0, r1 = blk * BLOCK_ROWS, min((blk + 1) * BLOCK_ROWS, nb)
+    g = torch.Generator(device=dev).manual_seed(1234 + blk)
+    rows = torch.randn(r1 - r0, D_DIM, device=dev, generator=g)
+    knn_b200.normalize_L2(rows)
+    return r0, r1, rows
+
+
+def fp64_parity(args, dev, rank, world, lo, hi, contributes, xq_s, D_s, I_s):
+    """Independent check of the engine's answer for the sampled queries xq_s (their (D, I) rows: D_s, I_s).
+
+    Every contributing rank regenerates its rows [lo, hi) block by block and scores the sample against them with a
+    plain torch fp64 matmul, keeping a running top-(k + 8) by (score desc, id asc).  The per-rank lists are
+    all-gathered and merged on rank 0 with the same rule.  Only torch ops on this side: no kernel, id mapping, bound
+    exchange or merge of the engine.  (With bf16 storage the rows are rounded to bf16 first: those values ARE the
+    database.)  Returns the record for the JSON line (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+
+    ns, k = xq_s.shape[0], args.k
+    kk = k + 8
+    q64 = xq_s.double()
+    best_s = torch.full((ns, kk), -float("inf"), dtype=torch.float64, device=dev)
+    best_i = torch.full((ns, kk), -1, dtype=torch.int64, device=dev)
+
+    def fold(bs, bi, cs, ci):
+        s_all, i_all = torch.cat([bs, cs], 1), torch.cat([bi, ci], 1)
+        # (score desc, id asc): stable sort by id first, then by score
+        o = torch.argsort(i_all, dim=1, stable=True)
+        s_all, i_all = torch.gather(s_all, 1, o), torch.gather(i_all, 1, o)
+        o = torch.argsort(s_all, dim=1, descending=True, stable=True)[:, :kk]
+        return torch.gather(s_all, 1, o), torch.gather(i_all, 1, o)
+
+    if contributes:
+        for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
+            r0, r1, rows = gen_block(blk, args.nb, dev)
+            s0, s1 = max(lo, r0), min(hi, r1)
+            rows = rows[s0 - r0:s1 - r0]
+            if args.bf16_storage:
+                rows = rows.bfloat16().float()
+            sc = q64 @ rows.double().T
+            top_s, top_p = torch.topk(sc, min(kk, sc.shape[1]), dim=1)
+            best_s, best_i = fold(best_s, best_i, top_s, top_p + s0)
+    if world > 1:
+        gs = torch.empty((world, ns, kk), dtype=torch.float64, device=dev)
+        gi = torch.empty((world, ns, kk), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gs, best_s)
+        dist.all_gather_into_tensor(gi, best_i)
+        best_s = torch.full((ns, kk), -float("inf"), dtype=torch.float64, device=dev)
+        best_i = torch.full((ns, kk), -1, dtype=torch.int64, device=dev)
+        for r in range(world):
+            best_s, best_i = fold(best_s, best_i, gs[r], gi[r])
+    if rank != 0:
+        return None
+    # ---- compare (rank 0) ----
+    d = D_DIM
+    tau = 2.0 * (d ** 0.5) * 2.0 ** -24  # unit vectors: scale |x||y| = 1
+    ref_s, ref_i = best_s[:, :k], best_i[:, :k]
+    differ = I_s != ref_i
+    # fp64 score of OUR id at a differing position: looked up in the reference's top-(k + 8); an id that is not even
+    # there lies beyond the (k + 8)-th fp64 candidate and counts as a mismatch
+    ids_sorted, order = torch.sort(best_i, dim=1)
+    at = torch.searchsorted(ids_sorted, I_s.contiguous()).clamp_(max=kk - 1)
+    found = torch.gather(ids_sorted, 1, at) == I_s
+    ours64 = torch.gather(torch.gather(best_s, 1, order), 1, at)
+    gap = (ours64 - ref_s).abs()
+    excused = differ & found & (gap <= tau)
+    beyond = differ & ~excused
+    dup = int(sum(len(set(r.tolist())) != k for r in I_s[:: max(1, ns // 64)].cpu()))
+    rel = ((D_s.double() - ref_s).abs() / ref_s.abs().clamp_min(1e-300))
+    rel = torch.where(excused | ~differ, rel, torch.zeros_like(rel))
+    return {"queries": int(ns), "k": int(k), "positions": int(ns * k), "id_mismatches_beyond_tau": int(beyond.sum().item()),
+            "excused": int(excused.sum().item()), "rows_with_duplicate_ids": dup, "max_rel_err_D": float(rel.max().item()),
+            "tau": tau, "rtol_D": 1e-5,
+            "reference": f"torch fp64 brute force over the regenerated rows of all {world} shard(s), top-(k+8) per shard, "
+                         "all-gather, merge on rank 0 (score desc, id asc)",
+            "ok": bool(beyond.sum().item() == 0 and dup == 0 and rel.max().item() <= 1e-5)}
 
 
 def main():
@@ -216,26 +324,33 @@ def main():
     if args.shadow_fmt and not args.bf16_storage:
         index.local.set_param("shadow_fmt", args.shadow_fmt)
     index.local.set_param("mantissa_bits", args.mantissa_bits)
+    if args.no_overlap:
+        index.local.set_param("overlap_finish", 0)
+        if Q == 1:
+            index.pipeline_batches = False
+        else:
+            index.inner.pipeline_batches = False
     index.local.reserve(hi - lo)
     for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
-        r0, r1 = blk * BLOCK_ROWS, min((blk + 1) * BLOCK_ROWS, args.nb)
-        g = torch.Generator(device=dev).manual_seed(1234 + blk)
-        rows = torch.randn(r1 - r0, D_DIM, device=dev, generator=g)
-        knn_b200.normalize_L2(rows)
+        r0, r1, rows = gen_block(blk, args.nb, dev)
         s0, s1 = max(lo, r0), min(hi, r1)
         index.local.add(rows[s0 - r0:s1 - r0])
     index.adopt_local(global_start=lo, n_global=args.nb)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t_build
 
-    g = torch.Generator(device=dev).manual_seed(4321)
-    xq_dev = torch.randn(args.nq, D_DIM, device=dev, generator=g)
-    knn_b200.normalize_L2(xq_dev)
+    if args.all_vs_all:  # C2 / C3: the queries are the database rows themselves (cath/search.py:24, pfam/proteins_search.py:49)
+        xq_dev = torch.cat([gen_block(blk, args.nb, dev)[2] for blk in range((args.nb + BLOCK_ROWS - 1) // BLOCK_ROWS)])[:args.nq].contiguous()
+    else:
+        g = torch.Generator(device=dev).manual_seed(4321)
+        xq_dev = torch.randn(args.nq, D_DIM, device=dev, generator=g)
+        knn_b200.normalize_L2(xq_dev)
     if not args.no_e2e:
         xq_host = torch.empty((args.nq, D_DIM), dtype=torch.float32, pin_memory=True)
         xq_host.copy_(xq_dev)
         D_host = torch.empty((args.nq, args.k), dtype=torch.float32, pin_memory=True)
         I_host = torch.empty((args.nq, args.k), dtype=torch.int64, pin_memory=True)
+        xq_np = xq_dev.cpu().numpy()  # pageable, what the reference's drivers hold
     torch.cuda.synchronize()
 
     lib = knn_b200._lib.load()
@@ -262,6 +377,16 @@ def main():
             if rank == 0:
                 D_host.copy_(D, non_blocking=True)
                 I_host.copy_(I, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def step_e2e_pageable():
+        if world == 1:
+            last["np"] = index.local.search(xq_np, args.k)  # IndexFlat.search(numpy) -> numpy: what `index.search` is to the drivers
+        else:
+            xq = index.upload_queries(xq_np) if Q == 1 else torch.from_numpy(xq_np).to(dev)
+            D, I = index.search(xq, args.k)
+            if rank == 0:
+                last["np"] = (D.cpu().numpy(), I.cpu().numpy())
             torch.cuda.synchronize()
 
     by_rank = {}
@@ -301,26 +426,39 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = args.nq * args.steps / (ms / 1e3)
     by_rank_value = dict(by_rank)  # per-rank step / GEMM time of the `value` leg (chip-to-chip spread under the power cap)
-
-    e2e = None
-    if not args.no_e2e:
-        ms_e, _, _, _ = timed(step_e2e, args.steps, 1)
-        h2d = args.nq * D_DIM * 4
-        d2h = args.nq * args.k * 12
-        e2e = {"value": args.nq * args.steps / (ms_e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps}
-
-    # parity spot check inside the bench: a few queries rescored exhaustively by the exact fp32 path
     D, I = last["DI"]  # result of the last timed step
     search_path = int(index.local.stat("path"))
     fmt_names = {1: "bf16", 2: "fp16"}
     fmt = fmt_names[int(index.local.stat("shadow_fmt"))]
     mbits = int(index.local.stat("mantissa_bits"))
-    chk = torch.arange(0, args.nq, max(1, args.nq // 64), device=dev)[:64]
+
+    e2e = e2e_pageable = None
+    if not args.no_e2e:
+        h2d = args.nq * D_DIM * 4
+        d2h = args.nq * args.k * 12
+        ms_e, _, _, _ = timed(step_e2e, args.steps, 1)
+        e2e = {"value": args.nq * args.steps / (ms_e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps, "host_memory": "pinned"}
+        ms_p, _, _, _ = timed(step_e2e_pageable, args.steps, 1)
+        e2e_pageable = {"value": args.nq * args.steps / (ms_p / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_p / args.steps,
+                        "host_memory": "pageable numpy arrays in and out (the reference drivers' call)"}
+
+    # ---- parity of the result of the last timed step against an fp64 brute force that shares nothing with the engine ----
+    ns = min(args.parity_queries, args.nq)
+    chk = torch.arange(ns, device=dev) * (args.nq // ns)
+    contributes = Q == 1 or rank // (world // Q) == 0  # with query groups every group holds the whole database: group 0 answers
+    parity = fp64_parity(args, dev, rank, world, lo, hi, contributes, xq_dev[chk].contiguous(), D[chk], I[chk])
+    if e2e_pageable and rank == 0 and parity is not None:  # the host path must return the same bits
+        Dn, In = last["np"]
+        parity["host_path_identical"] = bool(np.array_equal(Dn, D.cpu().numpy()) and np.array_equal(In, I.cpu().numpy()))
+        parity["ok"] = parity["ok"] and parity["host_path_identical"]
+    # ... and the engine's own exact fp32 path on a few of them (bit-identical by construction of the rerank)
+    chk2 = chk[:64]
     index.local.set_param("path", 1)
-    D1, I1 = index.search(xq_dev[chk].contiguous(), args.k)
+    D1, I1 = index.search(xq_dev[chk2].contiguous(), args.k)
     index.local.set_param("path", 0)
-    parity_ok = bool(torch.equal(I[chk], I1) and torch.equal(D[chk], D1))
+    parity_ok = bool(torch.equal(I[chk2], I1) and torch.equal(D[chk2], D1))
 
     phases = None
     if world > 1 and not args.no_phases:  # one extra, untimed step with CUDA events around the phases of the sharded search
@@ -328,6 +466,36 @@ def main():
         step_device()
         index.profile_phases = False
         phases = index.last_phases_ms
+
+    small = None
+    if world == 1 and not args.no_small_batch and not args.all_vs_all:
+        # Small query batches on the resident database: whole index.search calls (every launch of the call inside the
+        # timed region) against the HBM roofline; algorithmic bytes per SURVEY.md 8(d): N*d*2 + nq*d*4 + nq*k*12.
+        peaks_hbm = measured_peaks()["hbm_gbs"]
+        small = []
+        for nq_s in (1, 16, 64, 128, 256):
+            xs = xq_dev[:nq_s].contiguous()
+            search = index.local.search  # the product call (IndexFlat.search on a CUDA tensor)
+            for _ in range(3):
+                search(xs, args.k)
+            reps = 20
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = lib.knn_kernel_launches()
+            e0.record()
+            for _ in range(reps):
+                search(xs, args.k)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_call = e0.elapsed_time(e1) / reps
+            nbytes = args.nb * D_DIM * 2 + nq_s * D_DIM * 4 + nq_s * args.k * 12
+            gbs = nbytes / (ms_call / 1e3) / 1e9
+            launches_per_call = (lib.knn_kernel_launches() - l0) // reps
+            Ds, Is = search(xs, args.k)
+            small.append({"nq": nq_s, "ms_per_call": ms_call, "gbs": gbs, "frac_of_hbm": gbs / peaks_hbm,
+                          "launches_per_call": launches_per_call,
+                          "identical_to_large_batch_result": bool(torch.equal(Is, I[:nq_s]) and torch.equal(Ds, D[:nq_s]))})
+
     if rank == 0:
         peaks = measured_peaks()
         n_shard = hi - lo
@@ -344,7 +512,8 @@ def main():
                     "frac": (achieved / peak) if achieved else None, "peak_kind": "sustained, " + peaks["source"],
                     "frac_of_burst": (achieved / peaks["tflops_burst"]) if achieved else None,
                     "traffic": traffic, "traffic_note": traffic_note, "launches": gemm_launches, "kernel_ms_per_step": gemm_ms / args.steps,
-                    "algorithmic_flop_per_launch_avg": flops_per_step * args.steps / max(1, gemm_launches)}
+                    "algorithmic_flop_per_launch_avg": flops_per_step * args.steps / max(1, gemm_launches),
+                    "whole_step_frac_of_burst": 2.0 * args.nq * args.nb * D_DIM / world / (ms / args.steps / 1e3) / 1e12 / peaks["tflops_burst"]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_baseline
@@ -359,16 +528,24 @@ def main():
             "dtype": fmt, "dtype_note": f"{fmt} x {fmt} ({mbits} mantissa bits) -> f32 tensor-core filter (tcgen05 kind::f16), then exact f32 "
                                         "rescoring: results equal f32 IndexFlatIP",
             "data": "synthetic",
-            "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "config": workload_config(args, world), "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": launches, "roofline": roofline,
+            "parity_vs_fp64": parity, "small_batch": small,
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
             "search_path": search_path, "cta_group": args.cta_group, "phases_ms_rank0": phases, "ms_per_step_by_rank": by_rank_value or None,
             "shard_rows_by_rank": [b[r + 1] - b[r] for r in range(len(b) - 1)], "query_groups": Q,
             "rank_speed_weights": [round(w, 4) for w in weights] if weights else None,
+            "overlap_finish": not args.no_overlap,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        ok = torch.tensor([1 if (rank != 0 or (parity["ok"] and parity_ok)) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         dist.barrier()
         dist.destroy_process_group()
+        if int(ok.item()) == 0:
+            sys.exit(3)
+    elif not (parity["ok"] and parity_ok):
+        sys.exit(3)
 
 
 if __name__ == "__main__":

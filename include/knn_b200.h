@@ -18,6 +18,8 @@
  *     cudaStream_t passed as `stream` (NULL = default stream) and may synchronise it;
  *   - the caller owns all buffers; `add` copies (faiss semantics: the drivers reuse and
  *     mutate their arrays after add, pfam/proteins_search.py:37,49);
+ *   - an index is not re-entrant: calls on one index come from one thread at a time (the reference's drivers call
+ *     faiss sequentially); searches and adds on DIFFERENT streams are ordered against each other by the library;
  *   - the library is CUDA-only: it fails with KNN_ERR_CUDA when no sm_100 device is
  *     usable; there is no CPU fallback.
  */
@@ -37,7 +39,7 @@ extern "C" {
 #define KNN_ERR_INVALID (-1) /* bad argument (NULL, shape, k <= 0, ...) */
 #define KNN_ERR_CUDA (-2)    /* CUDA runtime / driver failure, or no usable device */
 #define KNN_ERR_MEMORY (-3)  /* device or host allocation failed */
-#define KNN_ERR_LIMIT (-4)   /* a documented limit was exceeded (k > KNN_MAX_K, ids >= 2^32) */
+#define KNN_ERR_LIMIT (-4)   /* a documented limit was exceeded (k > KNN_MAX_K, more than 2^31-1 rows in one index) */
 
 #define KNN_MAX_K 2048 /* reference uses k in {5,10,11,13,500,1000,2000} */
 
@@ -99,6 +101,24 @@ int knn_index_search_filter_dev(knn_index* idx, int64_t nq, const float* xq_dev,
                                 float* lower_j_dev, void* stream);
 int knn_index_search_finish_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, const float* lower_dev,
                                 float* D_dev, int64_t* I_dev, int64_t id_base, void* stream);
+
+/* The same two-phase search batch by batch, so that the caller can overlap the exchange + finish of one query batch
+ * with the filter of the next on a second stream (knn_b200/distributed.py does: filter of batch b on the main stream,
+ * event, then on a side stream all-reduce of that batch's bounds and finish_batch).
+ *   begin         fixes (nq, xq_dev, k) - xq_dev must stay valid until `end` - and returns the number of query batches
+ *                 and the rows per batch (the last batch may be shorter);
+ *   filter_batch  filters batch b and writes its bounds into bounds_dev, a caller-zeroed float array
+ *                 [nbatches][2][batch_rows]: [b][0][i] = lower bound of the k-th best true score of query
+ *                 b*batch_rows+i in this shard, [b][1][i] = MINUS the bound on the j-th best (j = ceil(k / shards)):
+ *                 ONE element-wise MAX all-reduce of the slice [b] over the shards combines both;
+ *   finish_batch  applies max([b][0], -[b][1]) and writes rows [b*batch_rows, ...) of this shard's (D, I);
+ *   end           after every batch has finished (stream-ordered): repairs overflowed queries, closes the search. */
+int knn_index_search_begin_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, int64_t* nbatches_out,
+                               int64_t* batch_rows_out, void* stream);
+int knn_index_search_filter_batch_dev(knn_index* idx, int64_t b, int64_t j, float* bounds_dev, void* stream);
+int knn_index_search_finish_batch_dev(knn_index* idx, int64_t b, const float* bounds_dev, float* D_dev, int64_t* I_dev,
+                                      int64_t id_base, void* stream);
+int knn_index_search_end_dev(knn_index* idx, float* D_dev, int64_t* I_dev, int64_t id_base, void* stream);
 
 /* Copy rows [i0, i0+n) back to the host as float32 (faiss Index::reconstruct_n); feeds
  * write_index (pfam/proteins_search.py:39-40). */
@@ -183,7 +203,9 @@ int knn_prefilter_emit_dev(int64_t nq, int64_t k, const int64_t* I_dev, const fl
  * with <= 64 queries use the few-queries variant of the GEMM kernel; default on), "gemm_stages", "panel_ratio".
  * Statistics of the last search: "path", "launches", "gemm_launches", "gemm_ms", "rerank_ms", "overflow_batches",
  * "overflow_queries"; of the index: "capacity", "shadow_fmt" (1 bf16, 2 fp16), "mantissa_bits",
- * "shadow_conversions" (times the shadow rows were rewritten in the other format). */
+ * "shadow_conversions" (times the shadow rows were rewritten in the other format).
+ * "overlap_finish" (default 1): a search of several query batches runs the exact rescoring of batch b on an internal
+ * side stream under the tensor-core filter of batch b + 1. */
 int knn_index_set_param(knn_index* idx, const char* name, int64_t value);
 int knn_index_get_stat(const knn_index* idx, const char* name, double* out);
 

@@ -38,6 +38,39 @@ void count_launch(int n = 1);
         KNN_CHECK_CUDA(cudaGetLastError());       \
     } while (0)
 
+// ---- device selection -----------------------------------------------------------------
+// Entry points never rely on the caller's current device: knn_index_* calls select the index's device, the
+// stateless *_dev calls select the device that owns the memory they are handed (PtrDeviceGuard).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    DeviceGuard() {}
+    explicit DeviceGuard(int dev) { select(dev); }
+    void select(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; }
+        if (ok && dev >= 0 && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// device ordinal that owns a device allocation (-1: not a device pointer / unknown: the current device stays)
+inline int device_of_pointer(const void* p) {
+    if (!p) return -1;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+struct PtrDeviceGuard : DeviceGuard {
+    explicit PtrDeviceGuard(const void* p) { select(device_of_pointer(p)); }
+};
+int num_sms();  // SM count of the CURRENT device (cached per device)
+
 // ---- layout constants -----------------------------------------------------------------
 constexpr int kDimAlign = 64;        // rows are padded with zeros to a multiple of 64 elements
 constexpr uint32_t kInvalidId = 0xFFFFFFFFu;
@@ -148,6 +181,7 @@ void gemm_plan_set_l2_hints(GemmPlan* p, int on);
 void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue);
 void gemm_plan_set_stages(GemmPlan* p, int stages);
 void gemm_plan_set_stream_kernel(GemmPlan* p, int on);   // few-queries variant for launches with <= 64 queries (default on)
+void gemm_plan_set_small_m128(GemmPlan* p, int on);      // 65..128 queries: single-CTA (M = 128) tiles (default on)
 int gemm_plan_query_rows_multiple(const GemmPlan* p);     // nq_pad granularity of the chosen variant
 // Scores queries (16-bit, format fmt_q, [nq_pad x dp]) against database rows [j0, j1) (16-bit, format fmt_db,
 // [ntotal x dp]) on the tensor cores and appends every (score, id) with score >= thr[q] to the candidate lists.
@@ -164,8 +198,10 @@ int launch_init_filter(FilterState st, int64_t nq, int64_t nq_pad, int first_cou
 // Two-phase (sharded) search: lower[q] = thr + eps on the way out; thr <- max(thr, lower - eps) on the way in.
 int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* lower, cudaStream_t s);
 // lower_j[q] = (j-th best approximate score in the list) - eps[q]
-int launch_kth_lower(FilterState st, const float* eps, int64_t nq, int j, float* lower_j, cudaStream_t s);
-int launch_apply_lower(float* thr, const float* eps, const float* lower, int64_t nq, cudaStream_t s);
+// (negate: the value is written with its sign flipped, so that an element-wise MAX reduction yields the MIN)
+int launch_kth_lower(FilterState st, const float* eps, int64_t nq, int j, bool negate, float* lower_j, cudaStream_t s);
+// thr <- max(thr, max(lower, -neg_lower2) - eps); neg_lower2 may be null
+int launch_apply_lower(float* thr, const float* eps, const float* lower, const float* neg_lower2, int64_t nq, cudaStream_t s);
 int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
 // Overflow repair: out[i] = xq[idx[i]] (rows of d floats); D[idx[i]] = Dt[i], I[idx[i]] = It[i] (rows of k).
 int launch_gather_rows(const float* xq, int d, const int* idx, int64_t n, float* out, cudaStream_t s);

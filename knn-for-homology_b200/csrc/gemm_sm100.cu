@@ -417,10 +417,11 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tc_fence_after();
             const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
             const int64_t q_warp0 = q - lane;  // query of lane 0 of this warp
+#ifdef KNN_EXPERIMENTS
+            // measurement aids (never compiled into the shipped library): 1 main loop only, 2 TMEM reads only,
+            // 3 TMEM reads + threshold compares with the survivors ignored
             if (args.debug_skip_epilogue == 1) {
-                // measurement aid: main loop only
             } else if (args.debug_skip_epilogue == 2) {
-                // measurement aid: TMEM reads only
                 uint32_t sink = 0;
 #pragma unroll 1
                 for (int cg = 0; cg < BN / 32; ++cg) {
@@ -431,7 +432,6 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
                 if (sink == 0x7fc12345u) args.counts[0] = 1;
             } else if (args.debug_skip_epilogue == 3) {
-                // measurement aid: TMEM reads + threshold compares, survivors ignored
                 uint32_t flagged = 0;
 #pragma unroll 1
                 for (int cg = 0; cg < BN / 32; ++cg) {
@@ -443,7 +443,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     if (__any_sync(0xffffffffu, any)) flagged |= 1u << cg;
                 }
                 if (flagged == 0xdeadbeefu) args.counts[0] = 1;
-            } else if constexpr (DENSE) {
+            } else
+#endif
+            if constexpr (DENSE) {
 #pragma unroll 1
                 for (int cg = 0; cg < BN / 32; ++cg) {
                     float v[32];
@@ -733,6 +735,7 @@ struct GemmPlan {
     int debug_skip_epilogue = 0;
     int stages = 0;     // 0: default depth (4)
     int stream_kernel = 1;  // launches with <= 64 queries use the few-queries variant (database rows as the M operand)
+    int small_m128 = 1;     // launches with 65..128 queries use the single-CTA (M = 128) variant of the main kernel
 };
 
 void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
@@ -740,6 +743,7 @@ void gemm_plan_set_l2_hints(GemmPlan* p, int on) { p->l2_hints = on; }
 void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue) { p->debug_skip_epilogue = skip_epilogue; }
 void gemm_plan_set_stages(GemmPlan* p, int stages) { p->stages = stages; }
 void gemm_plan_set_stream_kernel(GemmPlan* p, int on) { p->stream_kernel = on; }
+void gemm_plan_set_small_m128(GemmPlan* p, int on) { p->small_m128 = on; }
 int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
@@ -883,7 +887,10 @@ int gemm_filter_launch(GemmPlan* p, const h16_t* xq_h16, int fmt_q, int64_t nq, 
                        const h16_t* xb_h16, int fmt_db, int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1,
                        int metric, bool dense_first, FilterState st, cudaStream_t s) {
     if (j1 <= j0 || nq <= 0) return KNN_OK;
-    const int cg = p->cta_group;
+    // 65..128 queries: one CTA per tile (M = 128).  A CTA pair would pad them to M = 256 and spend twice the MMA time
+    // per database byte - at 256 queries tensor time and HBM time of a pass are equal (2 * 256 * d flop per 2 * d bytes
+    // = the machine balance), so the padded launch is tensor-bound where this one streams.
+    const int cg = (p->cta_group == 2 && nq <= BM && p->small_m128) ? 1 : p->cta_group;
     if (dp % BK != 0 || nq_pad % (BM * cg) != 0) {
         set_error("gemm_filter: dp (%d) must be a multiple of %d and nq_pad (%lld) of %d", dp, BK, (long long)nq_pad, BM * cg);
         return KNN_ERR_INVALID;

@@ -62,17 +62,39 @@ struct DevBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; }
-        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+struct PinBuf {  // page-locked host memory (bounce buffers of the host-pointer entry points)
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t want) {
+        if (want <= bytes) return KNN_OK;
+        release();
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            set_error("cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            return KNN_ERR_MEMORY;
+        }
+        bytes = want;
+        return KNN_OK;
     }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
     }
+    template <class T> T* as() const { return static_cast<T*>(p); }
 };
+
+// true when the driver can DMA straight to / from p (cudaHostAlloc / cudaHostRegister memory)
+inline bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
 
 }  // namespace knn
 
@@ -92,21 +114,36 @@ struct knn_index {
     DbStats* stats = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t add_event = nullptr;  // last ingest; searches on another stream wait on it
+    cudaEvent_t search_event = nullptr;  // end of the last search (it may rewrite the shadow rows / stats): adds and resets wait on it
     GemmPlan* plan = nullptr;
     // workspaces: exact path / staging
     DevBuf stage, xq_f32, xnorm2, eps, scores, lists_s, lists_i, overflow;
     DevBuf ovf_q, ovf_idx, ovf_x, ovf_D, ovf_I;  // per-query overflow flags of a call and the repair staging
     DevBuf h_xq, h_D, h_I;
+    // host-pointer search, pipelined per query batch (HostPipe below): two slots of device staging, pinned bounce
+    // buffers for pageable caller memory, one copy stream per direction
+    DevBuf hp_xq[2], hp_D[2], hp_I[2];
+    PinBuf hp_pin_xq[2], hp_pin_D[2], hp_pin_I[2];
+    DevBuf stage2;                      // second ingest staging buffer (knn_index_add double-buffers the H2D copies)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t hp_in_ready[2] = {nullptr, nullptr}, hp_out_done[2] = {nullptr, nullptr}, hp_computed[2] = {nullptr, nullptr};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};
     // tensor path: per-query state of the filter (queries, thresholds, candidate lists)
     struct TensorWs {
         DevBuf xq_f32, xq_h16, xnorm2, eps, thr, counts, cand_s, cand_i;
     };
-    TensorWs ws1;  // one query batch (single-call search)
-    TensorWs ws2;  // all queries of a two-phase search (filter ... exchange ... finish)
+    TensorWs ws1[2];  // one query batch each (single-call search): batch b filters in ws1[b & 1] while batch b - 1 finishes
+    TensorWs ws2;     // all queries of a two-phase search (filter ... exchange ... finish)
+    cudaStream_t side = nullptr;                  // finish phase of batch b runs here, under the GEMM of batch b + 1
+    cudaEvent_t ev_filtered[2] = {nullptr, nullptr};  // filter of the batch in ws1[i] done (main stream)
+    cudaEvent_t ev_finished[2] = {nullptr, nullptr};  // finish of the batch in ws1[i] done (side stream): ws1[i] reusable
+    int overlap_finish = 1;
     struct Pending {
         bool active = false, tensor = false;
         int64_t nq = 0, qb = 0, nbatches = 0;
         int k = 0, cap = 0;
+        const float* xq = nullptr;   // the caller's queries (kept alive by the caller until search_end)
+        long long launches0 = 0;
     } pend;
     // parameters
     int path_param = 0;
@@ -118,6 +155,7 @@ struct knn_index {
     int debug_skip_epilogue = 0;
     int gemm_stages = 0;
     int stream_kernel = 1;
+    int small_m128 = 1;
     int panel_ratio = 0;  // 0: automatic
     int64_t small_batch_nq = 256;  // batches up to this size use growth ratio 8
     int shadow_param = 0;          // 16-bit format of the tensor-core operands: 0 automatic (desired_shadow), 1 bf16, 2 fp16
@@ -148,17 +186,20 @@ void collect_profile(knn_index* ix) {
     }
 }
 
+constexpr int64_t kMaxRows = 0x7FFFFFFFll;
+
 bool bf16_only(const knn_index* ix) { return (ix->flags & KNN_FLAG_BF16_STORAGE) != 0; }
 
 int grow(knn_index* ix, int64_t want_rows, bool exact = false) {
     if (want_rows <= ix->capacity) return KNN_OK;
-    if (want_rows >= int64_t(0xFFFFFFFFll)) {
-        set_error("an index holds at most 2^32-2 rows");
+    if (want_rows > kMaxRows) {  // TMA row coordinates are signed 32-bit (gemm_sm100.cu); ids are stored as uint32
+        set_error("an index (one shard) holds at most 2^31-1 rows");
         return KNN_ERR_LIMIT;
     }
     int64_t cap = exact ? want_rows : ix->capacity + ix->capacity / 2;
     if (cap < want_rows) cap = want_rows;
     if (cap < 1024) cap = 1024;
+    if (cap > kMaxRows) cap = kMaxRows;
     // rows may have been ingested on a caller's stream: settle everything before moving them
     KNN_CHECK_CUDA(cudaDeviceSynchronize());
     float* nf = nullptr;
@@ -356,6 +397,7 @@ int tensor_prepare(knn_index* ix) {
     gemm_plan_set_debug(ix->plan, ix->debug_skip_epilogue);
     gemm_plan_set_stages(ix->plan, ix->gemm_stages);
     gemm_plan_set_stream_kernel(ix->plan, ix->stream_kernel);
+    gemm_plan_set_small_m128(ix->plan, ix->small_m128);
     return KNN_OK;
 }
 
@@ -411,10 +453,11 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
 // `lower` (optional) is a lower bound of the TRUE k-th best score per query obtained elsewhere (other shards):
 // a row can only be in the global top-k if its approximate score is >= lower - eps.
 int tensor_finish_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int64_t nb, int k, int cap, const float* lower,
-                        float* D, int64_t* I, int64_t id_base, cudaStream_t s) {
+                        const float* neg_lower2, float* D, int64_t* I, int64_t id_base, cudaStream_t s) {
     const int largest = ix->metric == KNN_METRIC_INNER_PRODUCT;
     FilterState st = filter_state(W, off, cap);
-    if (lower) KNN_CHECK(launch_apply_lower(st.thr, W.eps.as<float>() + off, lower, nb, s));
+    // the bound applied is max(lower, -neg_lower2) (either may be absent)
+    if (lower) KNN_CHECK(launch_apply_lower(st.thr, W.eps.as<float>() + off, lower, neg_lower2, nb, s));
     if (ix->profile) cudaEventRecord(next_event_r(ix), s);
     KNN_CHECK(launch_rerank(W.xq_f32.as<float>() + off * ix->dp, W.xnorm2.as<float>() + off, nb, ix->dp, ix->xb_f32,
                             bf16_rows(ix), ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
@@ -460,24 +503,178 @@ int redo_overflowed(knn_index* ix, int64_t nq, int64_t qb, int64_t nbatches, con
     return KNN_OK;
 }
 
+// Host-pointer search, pipelined (knn_index_search).  The reference's drivers hand index.search pageable numpy arrays
+// (cath/search.py:24, seqvec_search/main.py:45): per query batch the queries are staged into a pinned bounce buffer by
+// the calling thread, cross PCIe on a copy stream while the previous batch is on the tensor cores, and the batch's
+// (D, I) rows travel back on a second copy stream while the next batch is filtered.  Pinned caller memory is DMA'd
+// directly.  Everything is enqueued asynchronously; the host only ever waits for the slot it is about to reuse.
+struct HostPipe {
+    knn_index* ix;
+    const float* xq;
+    float* D;
+    int64_t* I;
+    int k;
+    bool in_pinned, out_pinned;
+    int64_t slot_q0[2] = {-1, -1}, slot_nb[2] = {0, 0};
+
+    int init(int64_t qb) {
+        const size_t in_bytes = size_t(qb) * ix->d * sizeof(float);
+        for (int w = 0; w < 2; ++w) {
+            KNN_CHECK(ix->hp_xq[w].ensure(in_bytes));
+            KNN_CHECK(ix->hp_D[w].ensure(size_t(qb) * k * sizeof(float)));
+            KNN_CHECK(ix->hp_I[w].ensure(size_t(qb) * k * sizeof(int64_t)));
+            if (!in_pinned) KNN_CHECK(ix->hp_pin_xq[w].ensure(in_bytes));
+            if (!out_pinned) {
+                KNN_CHECK(ix->hp_pin_D[w].ensure(size_t(qb) * k * sizeof(float)));
+                KNN_CHECK(ix->hp_pin_I[w].ensure(size_t(qb) * k * sizeof(int64_t)));
+            }
+        }
+        return KNN_OK;
+    }
+    // the results of the batch that last used slot w are in the caller's memory; the slot is free
+    int drain(int w) {
+        if (slot_q0[w] < 0) return KNN_OK;
+        KNN_CHECK_CUDA(cudaEventSynchronize(ix->hp_out_done[w]));
+        if (!out_pinned) {
+            memcpy(D + slot_q0[w] * k, ix->hp_pin_D[w].p, size_t(slot_nb[w]) * k * sizeof(float));
+            memcpy(I + slot_q0[w] * k, ix->hp_pin_I[w].p, size_t(slot_nb[w]) * k * sizeof(int64_t));
+        }
+        slot_q0[w] = -1;
+        return KNN_OK;
+    }
+    // before batch b: its queries on the way to the device, `s` ordered behind the copy
+    int acquire(int64_t b, int64_t q0, int64_t nb, cudaStream_t s, const float** xq_b, float** D_b, int64_t** I_b) {
+        const int w = int(b & 1);
+        KNN_CHECK(drain(w));
+        const size_t bytes = size_t(nb) * ix->d * sizeof(float);
+        const float* src = xq + q0 * ix->d;
+        if (!in_pinned) {
+            memcpy(ix->hp_pin_xq[w].p, src, bytes);
+            src = ix->hp_pin_xq[w].as<float>();
+        }
+        KNN_CHECK_CUDA(cudaMemcpyAsync(ix->hp_xq[w].p, src, bytes, cudaMemcpyHostToDevice, ix->copy_in));
+        KNN_CHECK_CUDA(cudaEventRecord(ix->hp_in_ready[w], ix->copy_in));
+        KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->hp_in_ready[w], 0));
+        *xq_b = ix->hp_xq[w].as<float>();
+        *D_b = ix->hp_D[w].as<float>();
+        *I_b = ix->hp_I[w].as<int64_t>();
+        return KNN_OK;
+    }
+    // after the finish phase of batch b was enqueued on `fs`: its rows on the way back
+    int release(int64_t b, int64_t q0, int64_t nb, cudaStream_t fs) {
+        const int w = int(b & 1);
+        KNN_CHECK_CUDA(cudaEventRecord(ix->hp_computed[w], fs));
+        KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->copy_out, ix->hp_computed[w], 0));
+        float* dD = out_pinned ? D + q0 * k : ix->hp_pin_D[w].as<float>();
+        int64_t* dI = out_pinned ? I + q0 * k : ix->hp_pin_I[w].as<int64_t>();
+        KNN_CHECK_CUDA(cudaMemcpyAsync(dD, ix->hp_D[w].p, size_t(nb) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->copy_out));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(dI, ix->hp_I[w].p, size_t(nb) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->copy_out));
+        KNN_CHECK_CUDA(cudaEventRecord(ix->hp_out_done[w], ix->copy_out));
+        slot_q0[w] = q0;
+        slot_nb[w] = nb;
+        return KNN_OK;
+    }
+    int finish() {
+        KNN_CHECK(drain(0));
+        KNN_CHECK(drain(1));
+        return KNN_OK;
+    }
+};
+
+// Overflow repair of a host-pointer search: the flagged queries (rare: heavily duplicated rows, out-of-range data) are
+// uploaded again, answered by the exact scan and written into the caller's rows.
+int redo_overflowed_host(knn_index* ix, int64_t nq, int64_t qb, int64_t nbatches, const float* xq, int k, float* D, int64_t* I,
+                         cudaStream_t s) {
+    std::vector<int> h_overflow(size_t(nbatches), 0);
+    KNN_CHECK_CUDA(cudaMemcpyAsync(h_overflow.data(), ix->overflow.p, sizeof(int) * size_t(nbatches), cudaMemcpyDeviceToHost, s));
+    KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    std::vector<int> redo, flags;
+    for (int64_t b = 0; b < nbatches; ++b) {
+        if (!h_overflow[size_t(b)]) continue;
+        const int64_t q0 = b * qb;
+        const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
+        ix->st_overflow_batches++;
+        flags.resize(size_t(nb));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(flags.data(), ix->ovf_q.as<int>() + q0, sizeof(int) * size_t(nb), cudaMemcpyDeviceToHost, s));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        for (int64_t i = 0; i < nb; ++i)
+            if (flags[size_t(i)]) redo.push_back(int(q0 + i));
+    }
+    ix->st_overflow_queries += (long long)redo.size();
+    const int64_t chunk = 1024;
+    std::vector<float> hx, hD;
+    std::vector<int64_t> hI;
+    for (size_t c0 = 0; c0 < redo.size(); c0 += size_t(chunk)) {
+        const int64_t n = int64_t(std::min(redo.size() - c0, size_t(chunk)));
+        KNN_CHECK(ix->ovf_x.ensure(sizeof(float) * size_t(chunk) * ix->d));
+        KNN_CHECK(ix->ovf_D.ensure(sizeof(float) * size_t(chunk) * k));
+        KNN_CHECK(ix->ovf_I.ensure(sizeof(int64_t) * size_t(chunk) * k));
+        hx.resize(size_t(n) * ix->d);
+        for (int64_t i = 0; i < n; ++i) memcpy(hx.data() + i * ix->d, xq + int64_t(redo[c0 + size_t(i)]) * ix->d, sizeof(float) * ix->d);
+        KNN_CHECK_CUDA(cudaMemcpyAsync(ix->ovf_x.p, hx.data(), sizeof(float) * hx.size(), cudaMemcpyHostToDevice, s));
+        KNN_CHECK(search_exact(ix, n, ix->ovf_x.as<float>(), k, ix->ovf_D.as<float>(), ix->ovf_I.as<int64_t>(), 0, s));
+        hD.resize(size_t(n) * k);
+        hI.resize(size_t(n) * k);
+        KNN_CHECK_CUDA(cudaMemcpyAsync(hD.data(), ix->ovf_D.p, sizeof(float) * hD.size(), cudaMemcpyDeviceToHost, s));
+        KNN_CHECK_CUDA(cudaMemcpyAsync(hI.data(), ix->ovf_I.p, sizeof(int64_t) * hI.size(), cudaMemcpyDeviceToHost, s));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        for (int64_t i = 0; i < n; ++i) {
+            memcpy(D + int64_t(redo[c0 + size_t(i)]) * k, hD.data() + i * k, sizeof(float) * k);
+            memcpy(I + int64_t(redo[c0 + size_t(i)]) * k, hI.data() + i * k, sizeof(int64_t) * k);
+        }
+    }
+    return KNN_OK;
+}
+
+// `hp` (host-pointer search): xq_dev / D / I are then HOST pointers that only the pipe touches.
 int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
-                  cudaStream_t s) {
+                  cudaStream_t s, HostPipe* hp = nullptr) {
     const int cap = candidate_capacity(k);
     int64_t qb = ix->query_batch;
     if (qb > nq) qb = nq;
     qb = round_up(qb, 256);
     const int64_t nbatches = (nq + qb - 1) / qb;
-    KNN_CHECK(tensor_ws_ensure(ix->ws1, qb, ix->dp, cap));
+    // The finish phase of a batch (exact rescoring + final select: HBM gathers and shared-memory sorts) runs on a
+    // side stream under the tensor-core filter of the next batch, which leaves HBM and most of every SM's registers
+    // idle; the two batches live in two workspaces.  One batch: nothing to overlap with.
+    const bool overlap = ix->overlap_finish && nbatches > 1;
+    KNN_CHECK(tensor_ws_ensure(ix->ws1[0], qb, ix->dp, cap));
+    if (overlap) KNN_CHECK(tensor_ws_ensure(ix->ws1[1], qb, ix->dp, cap));
     KNN_CHECK(ix->overflow.ensure(sizeof(int) * size_t(nbatches)));
     KNN_CHECK(ix->ovf_q.ensure(sizeof(int) * size_t(nq)));
     KNN_CHECK(tensor_prepare(ix));
+    if (hp) KNN_CHECK(hp->init(qb));
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(nbatches), s));
+    // a previous call's side-stream work (possibly issued from another stream) still owns the workspaces
+    KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[0], 0));
+    KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[1], 0));
     for (int64_t b = 0; b < nbatches; ++b) {
         const int64_t q0 = b * qb;
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
-        KNN_CHECK(tensor_filter_batch(ix, ix->ws1, 0, nb, xq_dev + q0 * ix->d, k, cap, ix->overflow.as<int>() + b,
-                                      ix->ovf_q.as<int>() + q0, s));
-        KNN_CHECK(tensor_finish_batch(ix, ix->ws1, 0, nb, k, cap, nullptr, D + q0 * k, I + q0 * k, id_base, s));
+        const int w = overlap ? int(b & 1) : 0;
+        const float* xq_b = hp ? nullptr : xq_dev + q0 * ix->d;
+        float* D_b = hp ? nullptr : D + q0 * k;
+        int64_t* I_b = hp ? nullptr : I + q0 * k;
+        if (hp) KNN_CHECK(hp->acquire(b, q0, nb, s, &xq_b, &D_b, &I_b));
+        if (overlap && b >= 2) KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[w], 0));  // ws1[w] is free again
+        KNN_CHECK(tensor_filter_batch(ix, ix->ws1[w], 0, nb, xq_b, k, cap, ix->overflow.as<int>() + b, ix->ovf_q.as<int>() + q0, s));
+        cudaStream_t fs = s;
+        if (overlap) {
+            fs = ix->side;
+            KNN_CHECK_CUDA(cudaEventRecord(ix->ev_filtered[w], s));
+            KNN_CHECK_CUDA(cudaStreamWaitEvent(fs, ix->ev_filtered[w], 0));
+        }
+        KNN_CHECK(tensor_finish_batch(ix, ix->ws1[w], 0, nb, k, cap, nullptr, nullptr, D_b, I_b, id_base, fs));
+        if (overlap) KNN_CHECK_CUDA(cudaEventRecord(ix->ev_finished[w], fs));
+        if (hp) KNN_CHECK(hp->release(b, q0, nb, fs));
+    }
+    if (overlap) {  // the caller's stream sees every result
+        KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[0], 0));
+        KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[1], 0));
+    }
+    if (hp) {
+        KNN_CHECK(hp->finish());
+        return redo_overflowed_host(ix, nq, qb, nbatches, xq_dev, k, D, I, s);
     }
     return redo_overflowed(ix, nq, qb, nbatches, xq_dev, k, D, I, id_base, s);
 }
@@ -489,7 +686,7 @@ bool use_tensor_path(const knn_index* ix, int64_t nq, int k) {
 }
 
 int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* D, int64_t* I, int64_t id_base,
-                    cudaStream_t s) {
+                    cudaStream_t s, HostPipe* hp = nullptr) {
     if (nq < 0 || k64 <= 0 || (nq > 0 && (!xq_dev || !D || !I))) {
         set_error("search: invalid arguments (nq=%lld, k=%lld)", (long long)nq, (long long)k64);
         return KNN_ERR_INVALID;
@@ -521,9 +718,14 @@ int search_dev_impl(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64,
         const bool tensor = use_tensor_path(ix, nq, k);
         ix->last_path = tensor ? 2 : 1;
         if (tensor) KNN_CHECK(prepare_shadow(ix, k, s));
-        rc = tensor ? search_tensor(ix, nq, xq_dev, k, D, I, id_base, s) : search_exact(ix, nq, xq_dev, k, D, I, id_base, s);
+        if (hp && !tensor) {
+            set_error("internal: host pipe on the exact path");
+            return KNN_ERR_INVALID;
+        }
+        rc = tensor ? search_tensor(ix, nq, xq_dev, k, D, I, id_base, s, hp) : search_exact(ix, nq, xq_dev, k, D, I, id_base, s);
     }
     if (rc != KNN_OK) return rc;
+    KNN_CHECK_CUDA(cudaEventRecord(ix->search_event, s));
     if (ix->profile && ix->ev_used) {
         KNN_CHECK_CUDA(cudaStreamSynchronize(s));
         collect_profile(ix);
@@ -555,6 +757,7 @@ int knn_normalize_l2_dev(float* x_dev, int64_t n, int64_t d, void* stream) {
         set_error("normalize_l2: invalid arguments");
         return KNN_ERR_INVALID;
     }
+    PtrDeviceGuard g(x_dev);
     return launch_normalize_l2(x_dev, n, d, static_cast<cudaStream_t>(stream));
 }
 
@@ -614,6 +817,20 @@ int knn_index_create(knn_index** out, int d, int metric, int device, unsigned fl
     ix->flags = flags;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->add_event, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->search_event, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->copy_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->copy_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ix->hp_in_ready[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->hp_out_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->hp_computed[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->stage_free[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ix->ev_filtered[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_finished[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&ix->stats, sizeof(DbStats));
     if (e == cudaSuccess) e = cudaMemset(ix->stats, 0, sizeof(DbStats));
     if (e != cudaSuccess) {
@@ -629,10 +846,20 @@ int knn_index_free(knn_index* ix) {
     if (!ix) return KNN_OK;
     DeviceGuard g(ix->device);
     cudaStreamSynchronize(ix->stream);
+    if (ix->side) cudaStreamSynchronize(ix->side);
     for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xnorm2, &ix->eps, &ix->scores, &ix->lists_s, &ix->lists_i,
                       &ix->overflow, &ix->ovf_q, &ix->ovf_idx, &ix->ovf_x, &ix->ovf_D, &ix->ovf_I, &ix->h_xq, &ix->h_D, &ix->h_I})
         b->release();
-    for (knn_index::TensorWs* W : {&ix->ws1, &ix->ws2})
+    for (int i = 0; i < 2; ++i) {
+        ix->hp_xq[i].release(); ix->hp_D[i].release(); ix->hp_I[i].release();
+        ix->hp_pin_xq[i].release(); ix->hp_pin_D[i].release(); ix->hp_pin_I[i].release();
+        for (cudaEvent_t e : {ix->hp_in_ready[i], ix->hp_out_done[i], ix->hp_computed[i], ix->stage_free[i]})
+            if (e) cudaEventDestroy(e);
+    }
+    ix->stage2.release();
+    if (ix->copy_in) cudaStreamDestroy(ix->copy_in);
+    if (ix->copy_out) cudaStreamDestroy(ix->copy_out);
+    for (knn_index::TensorWs* W : {&ix->ws1[0], &ix->ws1[1], &ix->ws2})
         for (DevBuf* b : {&W->xq_f32, &W->xq_h16, &W->xnorm2, &W->eps, &W->thr, &W->counts, &W->cand_s, &W->cand_i}) b->release();
     if (ix->xb_f32) cudaFree(ix->xb_f32);
     if (ix->xb_h16) cudaFree(ix->xb_h16);
@@ -641,6 +868,12 @@ int knn_index_free(knn_index* ix) {
     for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : ix->ev_pool_r) cudaEventDestroy(e);
     if (ix->add_event) cudaEventDestroy(ix->add_event);
+    if (ix->search_event) cudaEventDestroy(ix->search_event);
+    for (int i = 0; i < 2; ++i) {
+        if (ix->ev_filtered[i]) cudaEventDestroy(ix->ev_filtered[i]);
+        if (ix->ev_finished[i]) cudaEventDestroy(ix->ev_finished[i]);
+    }
+    if (ix->side) cudaStreamDestroy(ix->side);
     if (ix->plan) gemm_plan_destroy(ix->plan);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -653,6 +886,8 @@ int knn_index_reset(knn_index* ix) {
     ix->ntotal = 0;
     ix->stats_dirty = false;
     ix->fp16_unfit = false;
+    KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->stream, ix->search_event, 0));
+    KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->stream, ix->add_event, 0));
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->stats, 0, sizeof(DbStats), ix->stream));
     KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
     return KNN_OK;
@@ -674,6 +909,8 @@ int knn_index_add_dev(knn_index* ix, int64_t n, const float* x_dev, void* stream
     DeviceGuard g(ix->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     KNN_CHECK(grow(ix, ix->ntotal + n));
+    // a search still in flight on another stream may be rewriting the shadow rows and their statistics
+    KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->search_event, 0));
     const int64_t r0 = ix->ntotal;
     if (r0 == 0) {  // an empty index takes the format its expected size asks for; later rows follow the rows already there
         const ShadowChoice c = desired_shadow(ix, 0, std::max<int64_t>(ix->capacity, n));
@@ -697,14 +934,25 @@ int knn_index_add(knn_index* ix, int64_t n, const float* x) {
     if (n == 0) return KNN_OK;
     DeviceGuard g(ix->device);
     KNN_CHECK(grow(ix, ix->ntotal + n));
-    const int64_t rows_per = std::max<int64_t>(1, (int64_t(256) << 20) / (int64_t(ix->d) * 4));
-    KNN_CHECK(ix->stage.ensure(size_t(n < rows_per ? n : rows_per) * ix->d * sizeof(float)));
-    for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+    // chunks of <= 64 MiB through two staging buffers: the H2D copy of chunk i + 1 (copy stream) runs while chunk i is
+    // ingested (index stream); pageable caller memory goes through the driver's own bounce buffers
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t(64) << 20) / (int64_t(ix->d) * 4));
+    const size_t stage_bytes = size_t(n < rows_per ? n : rows_per) * ix->d * sizeof(float);
+    KNN_CHECK(ix->stage.ensure(stage_bytes));
+    if (n > rows_per) KNN_CHECK(ix->stage2.ensure(stage_bytes));
+    int64_t c = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows_per, ++c) {
         const int64_t nr = n - r0 < rows_per ? n - r0 : rows_per;
-        KNN_CHECK_CUDA(cudaMemcpyAsync(ix->stage.p, x + r0 * ix->d, size_t(nr) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-        KNN_CHECK(knn_index_add_dev(ix, nr, ix->stage.as<float>(), ix->stream));
-        KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));  // the staging buffer is reused; `add` copies (faiss semantics)
+        const int w = int(c & 1);
+        float* st = (w ? ix->stage2 : ix->stage).as<float>();
+        if (c >= 2) KNN_CHECK_CUDA(cudaEventSynchronize(ix->stage_free[w]));  // the ingest that read this buffer is done
+        KNN_CHECK_CUDA(cudaMemcpyAsync(st, x + r0 * ix->d, size_t(nr) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->copy_in));
+        KNN_CHECK_CUDA(cudaEventRecord(ix->hp_in_ready[w], ix->copy_in));
+        KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->stream, ix->hp_in_ready[w], 0));
+        KNN_CHECK(knn_index_add_dev(ix, nr, st, ix->stream));
+        KNN_CHECK_CUDA(cudaEventRecord(ix->stage_free[w], ix->stream));
     }
+    KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));  // `add` copies (faiss semantics): the caller may reuse x now
     return KNN_OK;
 }
 
@@ -733,7 +981,15 @@ int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, floa
     }
     if (nq == 0) return KNN_OK;
     DeviceGuard g(ix->device);
-    // host batches bound the device staging buffers; each is H2D -> search -> D2H on one stream
+    if (ix->ntotal > 0 && use_tensor_path(ix, nq, int(k))) {
+        // tensor path: one pipelined pass over the query batches (copies under compute, see HostPipe)
+        HostPipe hp{ix, xq, D, I, int(k), host_pointer_is_pinned(xq), host_pointer_is_pinned(D) && host_pointer_is_pinned(I)};
+        KNN_CHECK(search_dev_impl(ix, nq, xq, k, D, I, 0, ix->stream, &hp));
+        KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
+        return KNN_OK;
+    }
+    // exact path (small databases / few queries): host batches bound the device staging buffers; each is
+    // H2D -> search -> D2H on one stream
     const int64_t hb = 65536;
     const int64_t nb_max = nq < hb ? nq : hb;
     KNN_CHECK(ix->h_xq.ensure(size_t(nb_max) * ix->d * sizeof(float)));
@@ -762,22 +1018,23 @@ int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, floa
     return KNN_OK;
 }
 
-int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* lower_dev, int64_t j,
-                                float* lower_j_dev, void* stream) {
-    if (!ix || nq <= 0 || k64 <= 0 || !xq_dev || !lower_dev) {
-        set_error("search_filter: invalid arguments");
+// ---- two-phase (row-sharded) search ---------------------------------------------------------
+// begin -> per batch: filter_batch ... (caller combines the bounds of all shards) ... finish_batch -> end.
+// The batch-wise calls let the caller run exchange + finish of batch b on another stream under the filter of batch
+// b + 1 (knn_b200/distributed.py); knn_index_search_filter_dev / _finish_dev are the all-batches-at-once form.
+static int two_phase_begin(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, cudaStream_t s, const char* who) {
+    if (!ix || nq <= 0 || k64 <= 0 || !xq_dev) {
+        set_error("%s: invalid arguments", who);
         return KNN_ERR_INVALID;
     }
     if (k64 > KNN_MAX_K) {
-        set_error("search_filter: k=%lld exceeds KNN_MAX_K=%d", (long long)k64, KNN_MAX_K);
+        set_error("%s: k=%lld exceeds KNN_MAX_K=%d", who, (long long)k64, KNN_MAX_K);
         return KNN_ERR_LIMIT;
     }
     if (nq > (int64_t(1) << 17)) {
-        set_error("search_filter: at most 131072 queries per two-phase search (candidate lists stay resident)");
+        set_error("%s: at most 131072 queries per two-phase search (candidate lists stay resident)", who);
         return KNN_ERR_LIMIT;
     }
-    DeviceGuard g(ix->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int k = int(k64);
     KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->add_event, 0));
     ix->st_gemm_launches = 0;
@@ -791,11 +1048,13 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     P = knn_index::Pending();
     P.nq = nq;
     P.k = k;
+    P.xq = xq_dev;
+    P.launches0 = g_launches.load();
     P.tensor = ix->ntotal > 0 && use_tensor_path(ix, nq, k);
     ix->last_path = P.tensor ? 2 : 1;
-    if (!P.tensor) {  // exact path: nothing to filter, no bound to offer
-        KNN_CHECK(launch_fill_f32(lower_dev, nq, -FLT_MAX, s));
-        if (lower_j_dev) KNN_CHECK(launch_fill_f32(lower_j_dev, nq, -FLT_MAX, s));
+    if (!P.tensor) {  // exact path: nothing to filter, no bound to offer; one "batch" that finish runs in one go
+        P.qb = nq;
+        P.nbatches = 1;
         P.active = true;
         return KNN_OK;
     }
@@ -808,28 +1067,125 @@ int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
     KNN_CHECK(ix->ovf_q.ensure(sizeof(int) * size_t(nq)));
     KNN_CHECK(tensor_prepare(ix));
     KNN_CHECK_CUDA(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int) * size_t(P.nbatches), s));
-    for (int64_t b = 0; b < P.nbatches; ++b) {
-        const int64_t q0 = b * P.qb;
-        const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
-        KNN_CHECK(tensor_filter_batch(ix, ix->ws2, q0, nb, xq_dev + q0 * ix->d, k, P.cap, ix->overflow.as<int>() + b,
-                                      ix->ovf_q.as<int>() + q0, s));
+    P.active = true;
+    return KNN_OK;
+}
+
+// Filter of batch b.  lower[q] = thr + eps = (k-th best approximate score) - eps, a lower bound of the true k-th best
+// score of the shard; second bound (j >= 1): (j-th best approximate score) - eps - with G shards and j = ceil(k / G)
+// the MIN of it over the shards is a lower bound of the global k-th best (every shard holds j rows at or above it).
+// `negate_j`: the second bound is written negated, so that ONE element-wise MAX reduction combines both.
+static int two_phase_filter_batch(knn_index* ix, int64_t b, float* lower_b, int64_t j, float* lower_j_b, bool negate_j,
+                                  cudaStream_t s) {
+    auto& P = ix->pend;
+    const int64_t q0 = b * P.qb;
+    const int64_t nb = P.nq - q0 < P.qb ? P.nq - q0 : P.qb;
+    if (!P.tensor) {
+        KNN_CHECK(launch_fill_f32(lower_b, nb, -FLT_MAX, s));
+        if (lower_j_b) KNN_CHECK(launch_fill_f32(lower_j_b, nb, negate_j ? FLT_MAX : -FLT_MAX, s));
+        return KNN_OK;
     }
-    // lower[q] = thr + eps = (k-th best approximate score) - eps: a lower bound of the true k-th best score
-    KNN_CHECK(launch_export_lower(ix->ws2.thr.as<float>(), ix->ws2.eps.as<float>(), nq, lower_dev, s));
-    if (lower_j_dev) {
-        // second bound: (j-th best approximate score) - eps, j <= k.  With G shards and j = ceil(k / G) the MIN of
-        // it over the shards is a lower bound of the global k-th best (every shard holds j rows at or above it).
-        if (j < 1 || j > k) {
+    KNN_CHECK(tensor_filter_batch(ix, ix->ws2, q0, nb, P.xq + q0 * ix->d, P.k, P.cap, ix->overflow.as<int>() + b,
+                                  ix->ovf_q.as<int>() + q0, s));
+    KNN_CHECK(launch_export_lower(ix->ws2.thr.as<float>() + q0, ix->ws2.eps.as<float>() + q0, nb, lower_b, s));
+    if (lower_j_b) {
+        if (j < 1 || j > P.k) {
             set_error("search_filter: j must be in [1, k]");
             return KNN_ERR_INVALID;
         }
-        for (int64_t b = 0; b < P.nbatches; ++b) {
-            const int64_t q0 = b * P.qb;
-            const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
-            KNN_CHECK(launch_kth_lower(filter_state(ix->ws2, q0, P.cap), ix->ws2.eps.as<float>() + q0, nb, int(j), lower_j_dev + q0, s));
+        KNN_CHECK(launch_kth_lower(filter_state(ix->ws2, q0, P.cap), ix->ws2.eps.as<float>() + q0, nb, int(j), negate_j, lower_j_b, s));
+    }
+    return KNN_OK;
+}
+
+static int two_phase_finish_batch(knn_index* ix, int64_t b, const float* lower_b, const float* neg_lower2_b, float* D_dev,
+                                  int64_t* I_dev, int64_t id_base, cudaStream_t s) {
+    auto& P = ix->pend;
+    const int64_t q0 = b * P.qb;
+    const int64_t nb = P.nq - q0 < P.qb ? P.nq - q0 : P.qb;
+    if (!P.tensor) {
+        const long long l0 = P.launches0;
+        KNN_CHECK(search_dev_impl(ix, P.nq, P.xq, P.k, D_dev, I_dev, id_base, s));
+        P.launches0 = l0;
+        return KNN_OK;
+    }
+    return tensor_finish_batch(ix, ix->ws2, q0, nb, P.k, P.cap, lower_b, neg_lower2_b, D_dev + q0 * P.k, I_dev + q0 * P.k, id_base, s);
+}
+
+static int two_phase_end(knn_index* ix, float* D_dev, int64_t* I_dev, int64_t id_base, cudaStream_t s) {
+    auto& P = ix->pend;
+    P.active = false;
+    if (P.tensor) KNN_CHECK(redo_overflowed(ix, P.nq, P.qb, P.nbatches, P.xq, P.k, D_dev, I_dev, id_base, s));
+    KNN_CHECK_CUDA(cudaEventRecord(ix->search_event, s));
+    if (ix->profile && ix->ev_used) {
+        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        collect_profile(ix);
+    }
+    ix->st_launches = g_launches.load() - P.launches0;
+    return KNN_OK;
+}
+
+int knn_index_search_begin_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k, int64_t* nbatches_out,
+                               int64_t* batch_rows_out, void* stream) {
+    if (!ix || !nbatches_out || !batch_rows_out) {
+        set_error("search_begin: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    DeviceGuard g(ix->device);
+    KNN_CHECK(two_phase_begin(ix, nq, xq_dev, k, static_cast<cudaStream_t>(stream), "search_begin"));
+    *nbatches_out = ix->pend.nbatches;
+    *batch_rows_out = ix->pend.qb;
+    return KNN_OK;
+}
+
+int knn_index_search_filter_batch_dev(knn_index* ix, int64_t b, int64_t j, float* bounds_dev, void* stream) {
+    if (!ix || !bounds_dev || !ix->pend.active || b < 0 || b >= ix->pend.nbatches) {
+        set_error("search_filter_batch: no search_begin pending, batch out of range or null bounds");
+        return KNN_ERR_INVALID;
+    }
+    DeviceGuard g(ix->device);
+    float* base = bounds_dev + b * 2 * ix->pend.qb;
+    return two_phase_filter_batch(ix, b, base, j > 0 ? j : 1, base + ix->pend.qb, /*negate_j=*/true, static_cast<cudaStream_t>(stream));
+}
+
+int knn_index_search_finish_batch_dev(knn_index* ix, int64_t b, const float* bounds_dev, float* D_dev, int64_t* I_dev,
+                                      int64_t id_base, void* stream) {
+    if (!ix || !D_dev || !I_dev || !ix->pend.active || b < 0 || b >= ix->pend.nbatches) {
+        set_error("search_finish_batch: no search_begin pending, batch out of range or null output");
+        return KNN_ERR_INVALID;
+    }
+    DeviceGuard g(ix->device);
+    const float* base = bounds_dev ? bounds_dev + b * 2 * ix->pend.qb : nullptr;
+    return two_phase_finish_batch(ix, b, base, base ? base + ix->pend.qb : nullptr, D_dev, I_dev, id_base, static_cast<cudaStream_t>(stream));
+}
+
+int knn_index_search_end_dev(knn_index* ix, float* D_dev, int64_t* I_dev, int64_t id_base, void* stream) {
+    if (!ix || !D_dev || !I_dev || !ix->pend.active) {
+        set_error("search_end: no search_begin pending");
+        return KNN_ERR_INVALID;
+    }
+    DeviceGuard g(ix->device);
+    return two_phase_end(ix, D_dev, I_dev, id_base, static_cast<cudaStream_t>(stream));
+}
+
+int knn_index_search_filter_dev(knn_index* ix, int64_t nq, const float* xq_dev, int64_t k64, float* lower_dev, int64_t j,
+                                float* lower_j_dev, void* stream) {
+    if (!ix || !lower_dev) {
+        set_error("search_filter: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    DeviceGuard g(ix->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    KNN_CHECK(two_phase_begin(ix, nq, xq_dev, k64, s, "search_filter"));
+    auto& P = ix->pend;
+    for (int64_t b = 0; b < P.nbatches; ++b) {
+        const int64_t q0 = b * P.qb;
+        const int rc = two_phase_filter_batch(ix, b, lower_dev + q0, j, lower_j_dev ? lower_j_dev + q0 : nullptr, false, s);
+        if (rc != KNN_OK) {
+            P.active = false;
+            return rc;
         }
     }
-    P.active = true;
     return KNN_OK;
 }
 
@@ -840,28 +1196,20 @@ int knn_index_search_finish_dev(knn_index* ix, int64_t nq, const float* xq_dev, 
         return KNN_ERR_INVALID;
     }
     auto& P = ix->pend;
-    if (!P.active || P.nq != nq || P.k != int(k64)) {
+    if (!P.active || P.nq != nq || P.k != int(k64) || P.xq != xq_dev) {
         set_error("search_finish: no matching search_filter call is pending");
         return KNN_ERR_INVALID;
     }
     DeviceGuard g(ix->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    P.active = false;
-    if (!P.tensor) return search_dev_impl(ix, nq, xq_dev, k64, D_dev, I_dev, id_base, s);
-    const long long launches0 = g_launches.load();
     for (int64_t b = 0; b < P.nbatches; ++b) {
-        const int64_t q0 = b * P.qb;
-        const int64_t nb = nq - q0 < P.qb ? nq - q0 : P.qb;
-        KNN_CHECK(tensor_finish_batch(ix, ix->ws2, q0, nb, P.k, P.cap, lower_dev ? lower_dev + q0 : nullptr, D_dev + q0 * P.k,
-                                      I_dev + q0 * P.k, id_base, s));
+        const int rc = two_phase_finish_batch(ix, b, lower_dev ? lower_dev + b * P.qb : nullptr, nullptr, D_dev, I_dev, id_base, s);
+        if (rc != KNN_OK) {
+            P.active = false;
+            return rc;
+        }
     }
-    KNN_CHECK(redo_overflowed(ix, nq, P.qb, P.nbatches, xq_dev, P.k, D_dev, I_dev, id_base, s));
-    if (ix->profile && ix->ev_used) {
-        KNN_CHECK_CUDA(cudaStreamSynchronize(s));
-        collect_profile(ix);
-    }
-    ix->st_launches = g_launches.load() - launches0;
-    return KNN_OK;
+    return two_phase_end(ix, D_dev, I_dev, id_base, s);
 }
 
 int knn_index_reconstruct(knn_index* ix, int64_t i0, int64_t n, float* out) {
@@ -897,6 +1245,7 @@ int knn_merge_topk_dev(int metric, int64_t nq, int64_t k, int nlists, const floa
         set_error("merge: k=%lld exceeds KNN_MAX_K=%d", (long long)k, KNN_MAX_K);
         return KNN_ERR_LIMIT;
     }
+    PtrDeviceGuard g(D_out_dev);
     return launch_merge_lists(D_lists_dev, I_lists_dev, nlists, nq, int(k), metric == KNN_METRIC_INNER_PRODUCT, D_out_dev,
                               I_out_dev, static_cast<cudaStream_t>(stream));
 }
@@ -911,9 +1260,13 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "l2_hints") ix->l2_hints = value != 0;
     else if (n == "gemm_stages" && value >= 0 && value <= 6) ix->gemm_stages = int(value);
     else if (n == "stream_kernel") ix->stream_kernel = value != 0;
+    else if (n == "overlap_finish") ix->overlap_finish = value != 0;
+    else if (n == "small_m128") ix->small_m128 = value != 0;
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
     else if (n == "small_batch_nq" && value >= 0) ix->small_batch_nq = value;
+#ifdef KNN_EXPERIMENTS  // measurement aid that skips the epilogue (wrong results): never part of the shipped ABI
     else if (n == "debug_skip_epilogue") ix->debug_skip_epilogue = int(value);
+#endif
     else if (n == "shadow_fmt" && value >= 0 && value <= 2) {  // takes effect at the next search (prepare_shadow)
         if (bf16_only(ix) && value == 2) {
             set_error("set_param: an index with bf16 storage keeps bf16 rows");

@@ -23,17 +23,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
 int grid_for_rows(int64_t rows, int rows_per_block, int blocks_per_sm) {
     int64_t want = (rows + rows_per_block - 1) / rows_per_block;
     int64_t cap = int64_t(num_sms()) * blocks_per_sm;
@@ -382,6 +371,19 @@ rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, in
 }
 
 }  // namespace
+
+int num_sms() {
+    static int sms[64] = {};  // per device: the GPUs of one process need not be alike
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
+}
 
 // ---------------------------------------------------------------------------------------
 int launch_normalize_l2(float* x, int64_t n, int64_t d, cudaStream_t s) {

@@ -167,6 +167,14 @@ int knn_merge_topk_peer_dev(int metric, int64_t nq, int64_t k, int nranks, int64
         t.D_out[l] = static_cast<float*>(D_out_peer[l]);
         t.I_out[l] = static_cast<int64_t*>(I_out_peer[l]);
     }
+    // the calling rank's device owns its own output buffer; the pointer tables do not say which entry that is, so the
+    // stream decides (NULL stream: the caller's current device)
+    DeviceGuard dev_guard;
+    if (stream) {
+        int sdev = -1;
+        if (cudaStreamGetDevice(static_cast<cudaStream_t>(stream), &sdev) == cudaSuccess) dev_guard.select(sdev);
+        else cudaGetLastError();
+    }
     KNN_CHECK_CUDA(cudaFuncSetAttribute(merge_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (int64_t a = q0; a < q1; a += 65535 * 16) {  // grid.x limit is 2^31-1; chunking keeps launches bounded anyway

@@ -485,6 +485,7 @@ int knn_eval_family_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int32
                         const int32_t* db_family_dev, int64_t n_db, int32_t* lead_dev, int32_t* tp_dev, int* err_dev,
                         void* stream) {
     KNN_CHECK(check_hits("eval_family", nq, k, I_dev));
+    PtrDeviceGuard dev_guard(I_dev ? static_cast<const void*>(I_dev) : static_cast<const void*>(nullptr));
     if (nq == 0) return KNN_OK;
     if (!query_family_dev || !db_family_dev || !lead_dev || !tp_dev || !err_dev || n_db <= 0) {
         set_error("eval_family: null argument or empty database");
@@ -499,6 +500,7 @@ int knn_eval_family_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int32
 int knn_eval_levels_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int32_t* mapping_dev, int levels, int64_t n_db,
                         uint8_t* out_dev, int* err_dev, void* stream) {
     KNN_CHECK(check_hits("eval_levels", nq, k, I_dev));
+    PtrDeviceGuard dev_guard(I_dev ? static_cast<const void*>(I_dev) : static_cast<const void*>(nullptr));
     if (nq == 0) return KNN_OK;
     if (!mapping_dev || !out_dev || !err_dev || levels <= 0 || n_db < nq) {
         set_error("eval_levels: null argument, levels <= 0 or fewer label rows than queries");
@@ -518,6 +520,7 @@ int knn_eval_sets_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int64_t
                       const int64_t* set_members_dev, int64_t n_db_wrap, uint8_t* correct_dev, int32_t* lead_dev,
                       void* stream) {
     KNN_CHECK(check_hits("eval_sets", nq, k, I_dev));
+    PtrDeviceGuard dev_guard(I_dev ? static_cast<const void*>(I_dev) : static_cast<const void*>(nullptr));
     if (nq == 0) return KNN_OK;
     if (!set_offsets_dev || (!correct_dev && !lead_dev)) {
         set_error("eval_sets: null argument");
@@ -532,6 +535,7 @@ int knn_eval_sets_dev(int64_t nq, int64_t k, const int64_t* I_dev, const int64_t
 int knn_remove_self_hit_dev(int64_t nq, int64_t k, int64_t* I_dev, float* D_dev, const int64_t* self_ids_dev,
                             uint64_t* n_missing_dev, void* stream) {
     KNN_CHECK(check_hits("remove_self_hit", nq, k, I_dev));
+    PtrDeviceGuard dev_guard(I_dev ? static_cast<const void*>(I_dev) : static_cast<const void*>(nullptr));
     if (nq == 0) return KNN_OK;
     if (!n_missing_dev) {
         set_error("remove_self_hit: null counter");
@@ -547,6 +551,7 @@ int knn_prefilter_measure_dev(int64_t nq, int64_t k, const int64_t* I_dev, const
                               const int64_t* test_map_dev, int64_t n_test, const int64_t* train_map_dev, int64_t n_train,
                               int clip, int64_t* sec_off_dev, int64_t* idx_off_dev, int* err_dev, void* stream) {
     KNN_CHECK(check_hits("prefilter_measure", nq, k, I_dev));
+    PtrDeviceGuard dev_guard(I_dev ? static_cast<const void*>(I_dev) : static_cast<const void*>(nullptr));
     if (!sec_off_dev || !idx_off_dev || !err_dev || (nq > 0 && (!D_dev || !test_map_dev || !train_map_dev)) || n_test <= 0 ||
         n_train <= 0) {
         set_error("prefilter_measure: null argument or empty id map");
@@ -576,6 +581,7 @@ int knn_prefilter_emit_dev(int64_t nq, int64_t k, const int64_t* I_dev, const fl
                            int clip, const int64_t* sec_off_dev, const int64_t* idx_off_dev, uint8_t* data_dev,
                            uint8_t* index_dev, int* err_dev, void* stream) {
     KNN_CHECK(check_hits("prefilter_emit", nq, k, I_dev));
+    PtrDeviceGuard dev_guard(I_dev ? static_cast<const void*>(I_dev) : static_cast<const void*>(nullptr));
     if (nq == 0) return KNN_OK;
     if (!D_dev || !test_map_dev || !train_map_dev || !sec_off_dev || !idx_off_dev || !data_dev || !index_dev || !err_dev) {
         set_error("prefilter_emit: null argument");

@@ -482,7 +482,7 @@ tighten_warp_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __
 // score >= lower_j[q].  One warp per query; -FLT_MAX when the list holds fewer than j entries.
 __global__ void __launch_bounds__(256)
 kth_lower_kernel(const float* __restrict__ cand_scores, const int* __restrict__ counts, int cap,
-                 const float* __restrict__ eps, int64_t nq, int j, float* __restrict__ lower_j) {
+                 const float* __restrict__ eps, int64_t nq, int j, int negate, float* __restrict__ lower_j) {
     const int lane = threadIdx.x & 31;
     const int64_t q = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -495,7 +495,7 @@ kth_lower_kernel(const float* __restrict__ cand_scores, const int* __restrict__ 
         out = from_orderable_f32(kth) - e;
         if (!(out == out)) out = -FLT_MAX;
     }
-    if (lane == 0) lower_j[q] = out;
+    if (lane == 0) lower_j[q] = negate ? -out : out;
 }
 
 // k-way merge of up to 32 SORTED lists by one warp per query: lane l owns list l and its head; every round the
@@ -552,10 +552,15 @@ __global__ void export_lower_kernel(const float* __restrict__ thr, const float* 
 }
 
 __global__ void apply_lower_kernel(float* __restrict__ thr, const float* __restrict__ eps, const float* __restrict__ lower,
-                                   int64_t nq) {
+                                   const float* __restrict__ neg_lower2, int64_t nq) {
     const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    const float l = lower[q], e = eps[q];
+    float l = lower[q];
+    const float e = eps[q];
+    if (neg_lower2) {  // the caller's bound is max(lower, -neg_lower2)
+        const float l2 = -neg_lower2[q];
+        if (l2 > l) l = l2;
+    }
     if (l > -FLT_MAX && e < FLT_MAX) {
         const float t = l - e;
         if (t > thr[q]) thr[q] = t;
@@ -653,14 +658,14 @@ int launch_export_lower(const float* thr, const float* eps, int64_t nq, float* l
     return KNN_OK;
 }
 
-int launch_kth_lower(FilterState st, const float* eps, int64_t nq, int j, float* lower_j, cudaStream_t s) {
-    kth_lower_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(st.cand_scores, st.counts, st.cap, eps, nq, j, lower_j);
+int launch_kth_lower(FilterState st, const float* eps, int64_t nq, int j, bool negate, float* lower_j, cudaStream_t s) {
+    kth_lower_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(st.cand_scores, st.counts, st.cap, eps, nq, j, negate ? 1 : 0, lower_j);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }
 
-int launch_apply_lower(float* thr, const float* eps, const float* lower, int64_t nq, cudaStream_t s) {
-    apply_lower_kernel<<<unsigned((nq + 255) / 256), 256, 0, s>>>(thr, eps, lower, nq);
+int launch_apply_lower(float* thr, const float* eps, const float* lower, const float* neg_lower2, int64_t nq, cudaStream_t s) {
+    apply_lower_kernel<<<unsigned((nq + 255) / 256), 256, 0, s>>>(thr, eps, lower, neg_lower2, nq);
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }

@@ -36,6 +36,10 @@ SIGNATURES = {
     "knn_index_search_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "knn_index_search_filter_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "knn_index_search_finish_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "knn_index_search_begin_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp]),
+    "knn_index_search_filter_batch_dev": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "knn_index_search_finish_batch_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "knn_index_search_end_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "knn_index_reconstruct": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
     "knn_merge_topk_dev": (ctypes.c_int, [ctypes.c_int, c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "knn_peer_buffer_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i64, ctypes.c_int]),

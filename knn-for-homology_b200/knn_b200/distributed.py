@@ -201,6 +201,7 @@ def measured_rank_speeds(d: int, device: int, group=None, seconds: float = 1.5, 
 
 class ShardedIndexFlat:
     TWO_PHASE_MAX_QUERIES = 131072  # limit of knn_index_search_filter_dev (candidate lists stay resident)
+    MAX_TOTAL_ROWS = 2 ** 32 - 1
 
     def __init__(self, d: int, metric: int, group=None, device=None, index_factory=None, merge_fn=None,
                  exchange_bounds: bool = True, peer_merge: bool = True, shard_weights=None, **index_kw):
@@ -224,6 +225,8 @@ class ShardedIndexFlat:
         self.exchange_bounds = exchange_bounds
         self.peer_merge = peer_merge  # exchange + merge in one kernel over NVLink peer memory (CUDA results only)
         self._exchange = None
+        self._side_stream = None
+        self.pipeline_batches = True  # exchange + finish of query batch b on a side stream under the filter of batch b + 1
         self.profile_phases = False
         self.last_phases_ms = None
         self.last_stats = None
@@ -255,16 +258,29 @@ class ShardedIndexFlat:
         """For data generated per shard: this rank's rows are x_local, their global ids start at
         global_start; n_global rows are being added across all ranks."""
         cnt = x_local.shape[0]
+        self._check_total(int(n_global))
         if cnt:
             self.local.add(x_local)
         self._segments.append((int(global_start), self._nlocal, cnt))
         self._nlocal += cnt
         self._ntotal += int(n_global)
 
+    def _check_total(self, n_more: int) -> None:
+        # the cross-shard merges build their keys from 32-bit ids (csrc/select.cu, csrc/peer.cu)
+        if self._ntotal + n_more >= self.MAX_TOTAL_ROWS:
+            raise ValueError("a sharded index holds at most 2^32-2 rows in total (global ids are merged as 32-bit keys)")
+
+    def close(self) -> None:
+        """Releases the NVLink exchange buffer and the peers' IPC mappings.  Collective over the group."""
+        if self._exchange is not None:
+            self._exchange.close()
+            self._exchange = None
+
     def adopt_local(self, global_start: int, n_global: int) -> None:
         """Book-keeping for rows that were added straight into ``self.local`` (e.g. generated
         block by block on the device): they become one segment starting at global_start."""
         cnt = self.local.ntotal - self._nlocal
+        self._check_total(int(n_global))
         self._segments.append((int(global_start), self._nlocal, cnt))
         self._nlocal += cnt
         self._ntotal += int(n_global)
@@ -273,9 +289,11 @@ class ShardedIndexFlat:
         """local row numbers -> global row numbers, -1 kept."""
         import torch
 
+        if not self._segments:  # searched before any add: all padding
+            return I
         if len(self._segments) == 1:
             g0 = self._segments[0][0]
-            return torch.where(I >= 0, I + g0, I)
+            return torch.where(I >= 0, I + g0, I) if g0 else I
         starts = torch.tensor([s[1] for s in self._segments], device=I.device, dtype=I.dtype)
         offs = torch.tensor([s[0] - s[1] for s in self._segments], device=I.device, dtype=I.dtype)
         seg = torch.bucketize(I.clamp(min=0), starts, right=True) - 1
@@ -350,7 +368,12 @@ class ShardedIndexFlat:
         mark("start")
         two_phase = (self.world > 1 and self.exchange_bounds and hasattr(self.local, "search_filter")
                      and x.shape[0] <= self.TWO_PHASE_MAX_QUERIES)
-        if two_phase:
+        globalised = False
+        if two_phase and self.pipeline_batches and hasattr(self.local, "search_begin"):
+            xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if as_numpy else x
+            D, I = self._two_phase_pipelined(xd, k, mark)
+            globalised = len(self._segments) == 1
+        elif two_phase:
             # filter on every shard -> all-reduce(MAX) of the per-query lower bounds of the k-th best score ->
             # each shard rescoring only what can still be in the global top-k
             xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if as_numpy else x
@@ -374,7 +397,8 @@ class ShardedIndexFlat:
                 if backend == "nccl":
                     dev = torch.device("cuda", self.local.device)
                     D, I = D.to(dev), I.to(dev)
-        I = self._to_global(I)
+        if not globalised:
+            I = self._to_global(I)
         mark("to_global")
         if self.world > 1 and self.peer_merge and D.is_cuda and self.world <= 16 and (self.world + 1) * k * 8 <= 200 * 1024:
             D, I = self._merge_over_peer_memory(D, I)
@@ -393,6 +417,45 @@ class ShardedIndexFlat:
             self.last_phases_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
         if as_numpy:
             return D.cpu().numpy(), I.cpu().numpy()
+        return D, I
+
+    def _two_phase_pipelined(self, xd, k: int, mark):
+        """The two-phase search, one query batch at a time over two streams.  Main stream: tensor-core filter of
+        batch 0, 1, 2 ...  Side stream, per batch as soon as its filter is done: ONE all-reduce(MAX) of the batch's two
+        bounds (a few hundred KB over NVLink), then the finish phase (exact rescoring of what can still be in the
+        global top-k, final select).  The finish phase is HBM gathers and shared-memory sorts, the filter is tensor-core
+        work that leaves HBM idle, so the two share the SMs; the collective's wait for the slowest shard of batch b is
+        hidden under this rank's own filter of batch b + 1.  Only the last batch's exchange + finish is exposed.
+        With a single add() segment the global id base goes into the kernels (id_base), sparing a pass over I."""
+        import torch
+
+        dev = torch.device("cuda", self.local.device)
+        main = torch.cuda.current_stream(dev)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        side = self._side_stream
+        nq = xd.shape[0]
+        nbatches, rows = self.local.search_begin(xd, k)
+        bounds = torch.zeros((nbatches, 2, rows), dtype=torch.float32, device=dev)
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        id_base = self._segments[0][0] if len(self._segments) == 1 else 0
+        j = -(-k // self.world)
+        side.wait_stream(main)  # bounds / D / I exist (allocator streams) before the side stream touches them
+        for b in range(nbatches):
+            self.local.search_filter_batch(b, j, bounds)
+            filtered = torch.cuda.Event()
+            filtered.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(filtered)
+                self._dist.all_reduce(bounds[b], op=self._dist.ReduceOp.MAX, group=self.group)
+                self.local.search_finish_batch(b, bounds, D, I, id_base)
+        mark("filter")
+        main.wait_stream(side)
+        for t in (bounds, D, I):
+            t.record_stream(side)
+        mark("exchange_finish_exposed")
+        self.local.search_end(D, I, id_base)
         return D, I
 
     def _merge_over_peer_memory(self, D, I):
@@ -498,6 +561,9 @@ class GridIndexFlat:
             return D, I
         if as_numpy:
             D, I = torch.from_numpy(D), torch.from_numpy(I)
+            if self._dist.get_backend(self.col_group) == "nccl":  # the column all-gather moves device tensors
+                dev = torch.device("cuda", self.inner.local.device)
+                D, I = D.to(dev), I.to(dev)
         b = self.query_bounds(n)
         chunk = max(b[g + 1] - b[g] for g in range(self.Q))  # equal chunks for all_gather_into_tensor; tails are padding
         bufD = torch.empty((self.Q * chunk, k), dtype=D.dtype, device=D.device)
@@ -510,5 +576,8 @@ class GridIndexFlat:
         D = torch.cat([bufD[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
         I = torch.cat([bufI[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
         if as_numpy:
-            return D.numpy(), I.numpy()
+            return D.cpu().numpy(), I.cpu().numpy()
         return D, I
+
+    def close(self) -> None:
+        self.inner.close()

@@ -7,6 +7,7 @@ crosses the host/device boundary for every step (normalize_L2: up and down, add:
   search_and_save   cath/search.py:29-53
   faiss_search      seqvec_search/main.py:22-50
   proteins_search   pfam/proteins_search.py:11-57 (flat branch)
+  create_index      seqvec_search/create_index.py:16-47 (index build + persist; flat index instead of LSH)
 
 Results are bit-identical to calling the faiss-style API step by step (same kernels, same order).
 """
@@ -19,6 +20,13 @@ import numpy as np
 
 from .index import METRIC_INNER_PRODUCT, METRIC_L2, IndexFlat, _default_device, normalize_L2
 from .io import write_index
+
+# What users of the approximate branches get: the exact index answers every query the
+# approximate ones answer, with better neighbours, and on this hardware faster than a Hamming scan would
+#  - so the message points there instead of failing silently or returning other results.
+APPROXIMATE_INDEX_HINT = ("%s is an approximate index and not part of this engine (its codes depend on faiss's own random "
+                          "rotation, so results could never match the reference's); use the exact 'flat' index - on a "
+                          "B200 it is faster than the Hamming scan it would replace")
 
 
 def _upload(x: np.ndarray, device: int):
@@ -115,7 +123,7 @@ def proteins_search(full_sequences_data: Path, index_mode: str = "flat", k: int 
     """pfam/proteins_search.py:11-57, flat branch: `full_sequences.npy` -> `full_sequences_flat.index`,
     `full_sequences_flat_scores.npy`, `full_sequences_flat_hits.npy` in the same directory."""
     if index_mode != "flat":
-        raise ValueError(index_mode + ": only the exact flat index is part of this engine")
+        raise ValueError(APPROXIMATE_INDEX_HINT % {"lsh": "IndexLSH", "hnsw": "IndexHNSWFlat"}.get(index_mode, repr(index_mode)))
     device = _default_device() if device is None else device
     full_sequences_data = Path(full_sequences_data)
     npy = full_sequences_data.joinpath("full_sequences.npy")
@@ -137,3 +145,41 @@ def proteins_search(full_sequences_data: Path, index_mode: str = "flat", k: int 
     np.save(full_sequences_data.joinpath(f"full_sequences_{index_mode}_scores.npy"), flat_scores)
     np.save(full_sequences_data.joinpath(f"full_sequences_{index_mode}_hits.npy"), flat_hits)
     return flat_scores, flat_hits
+
+
+def create_index(args=None):
+    """seqvec_search/create_index.py:16-47: `<dir>/train.npy` -> an index file that `main.py --knn-index`
+    (seqvec_search/main.py:131-132: `faiss.read_index`) loads and hands to `faiss_search`.
+
+    Same command line (`--dir`, `--index`, `--param`).  The reference builds an `IndexLSH(d, param)` here; this engine
+    is the exact one, so the file written is a FLAT inner-product index (`IxFI`, faiss's on-disk format): `--param`
+    (LSH bits) is accepted and has no meaning for it.  `faiss_search` normalises a matrix haystack in place before
+    adding it (main.py:34) but takes a ready index as it is, so the rows are L2-normalised here, on the device, before
+    they are added - searching the file gives exactly what searching `train.npy` gives.  `--kind lsh` raises.
+    Returns the index (the reference returns None)."""
+    import argparse
+    import logging
+
+    logger = logging.getLogger(__name__)
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--dir", type=Path, default=Path(), help="The name of the directory containing the database")
+    parser.add_argument("--index", type=Path, required=True, help="The location to write the index to")
+    parser.add_argument("--param", type=int, default=1024,
+                        help="The tuning parameter of the (LSH) index of the reference; ignored by the exact flat index")
+    parser.add_argument("--kind", default="flat", choices=["flat", "lsh"], help="flat: exact index (this engine)")
+    parser.add_argument("--device", type=int, default=None)
+    args = parser.parse_args(args)
+    if args.kind != "flat":
+        raise NotImplementedError(APPROXIMATE_INDEX_HINT % "IndexLSH")
+    device = _default_device() if args.device is None else args.device
+    logger.info(f"Loading database from {args.dir.joinpath('train.npy')}")
+    embeddings = np.load(str(args.dir.joinpath("train.npy")))
+    logger.info(f"Building exact flat index on {embeddings.shape}")
+    x = _upload(embeddings, device)
+    normalize_L2(x)
+    index = IndexFlat(x.shape[1], METRIC_INNER_PRODUCT, device=device)
+    index.train(x)
+    index.add(x)
+    logger.info("Writing out the flat index")
+    write_index(index, str(args.index))
+    return index

@@ -43,6 +43,24 @@ def _torch_stream(device: int) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_PINNED_RESULT_LIMIT = 1 << 30
+
+
+def _result_arrays(nq: int, k: int):
+    """(D, I) numpy arrays for a host-path search.  Up to 1 GiB they live in page-locked memory (owned by a torch
+    tensor the arrays keep alive), so the library DMAs the result rows straight into them under the search of the next
+    query batch instead of bouncing them through a staging buffer; they are ordinary numpy arrays to the caller."""
+    if 0 < nq * k * 12 <= _PINNED_RESULT_LIMIT:
+        try:
+            import torch
+
+            return (torch.empty((nq, k), dtype=torch.float32, pin_memory=True).numpy(),
+                    torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy())
+        except Exception:
+            pass
+    return np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int64)
+
+
 def normalize_L2(x) -> None:
     """In-place row normalisation, faiss.normalize_L2 (cath/search.py:19, seqvec_search/main.py:31,34).
 
@@ -155,8 +173,7 @@ class IndexFlat:
                                                       int(id_base), _torch_stream(self.device)))
             return D, I
         x = self._host_matrix(x)
-        D = np.empty((x.shape[0], k), dtype=np.float32)
-        I = np.empty((x.shape[0], k), dtype=np.int64)
+        D, I = _result_arrays(x.shape[0], k)
         _lib.check(self._lib.knn_index_search(self._h, x.shape[0], x.ctypes.data, k, D.ctypes.data, I.ctypes.data))
         if id_base:
             I[I >= 0] += int(id_base)
@@ -191,6 +208,28 @@ class IndexFlat:
         _lib.check(self._lib.knn_index_search_finish_dev(self._h, x.shape[0], x.data_ptr(), int(k), lower.data_ptr(),
                                                          D.data_ptr(), I.data_ptr(), int(id_base), _torch_stream(self.device)))
         return D, I
+
+    # -- the same, batch by batch (the caller overlaps exchange + finish of batch b with the filter of batch b + 1) --
+    def search_begin(self, x, k: int):
+        """Returns (nbatches, batch_rows); x is kept alive until search_end."""
+        x = self._dev_matrix(x)
+        nb, rows = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._lib.knn_index_search_begin_dev(self._h, x.shape[0], x.data_ptr(), int(k), ctypes.byref(nb),
+                                                        ctypes.byref(rows), _torch_stream(self.device)))
+        self._pending_x = x
+        return nb.value, rows.value
+
+    def search_filter_batch(self, b: int, j: int, bounds) -> None:
+        """bounds: zero-initialised float32 CUDA tensor (nbatches, 2, batch_rows); slice [b] is written."""
+        _lib.check(self._lib.knn_index_search_filter_batch_dev(self._h, int(b), int(j), bounds.data_ptr(), _torch_stream(self.device)))
+
+    def search_finish_batch(self, b: int, bounds, D, I, id_base: int = 0) -> None:
+        _lib.check(self._lib.knn_index_search_finish_batch_dev(self._h, int(b), bounds.data_ptr() if bounds is not None else None,
+                                                               D.data_ptr(), I.data_ptr(), int(id_base), _torch_stream(self.device)))
+
+    def search_end(self, D, I, id_base: int = 0) -> None:
+        _lib.check(self._lib.knn_index_search_end_dev(self._h, D.data_ptr(), I.data_ptr(), int(id_base), _torch_stream(self.device)))
+        self._pending_x = None
 
     def search_into(self, xq_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int) -> None:
         """Host-pointer search into caller-owned (e.g. pinned) buffers: the raw C-ABI call."""
@@ -227,12 +266,16 @@ class IndexLSH:
     index itself is approximate and outside the flat path."""
 
     def __init__(self, *a, **kw):
-        raise NotImplementedError("IndexLSH is not part of the flat-search path this engine replaces")
+        from .drivers import APPROXIMATE_INDEX_HINT
+
+        raise NotImplementedError(APPROXIMATE_INDEX_HINT % "IndexLSH")
 
 
 class IndexHNSWFlat:
     def __init__(self, *a, **kw):
-        raise NotImplementedError("IndexHNSWFlat is not part of the flat-search path this engine replaces")
+        from .drivers import APPROXIMATE_INDEX_HINT
+
+        raise NotImplementedError(APPROXIMATE_INDEX_HINT % "IndexHNSWFlat")
 
 
 def merge_topk(D_lists, I_lists, metric: int):

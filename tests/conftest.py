@@ -27,3 +27,17 @@ def expected():
     import numpy as np
 
     return dict(np.load(GOLDEN / "expected.npz"))
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Totals of every oracle parity check of the run: positions compared, tie-excused positions, worst relative
+    distance error (BASELINE.json's bar: ids identical except at ties, distances within 1e-5 relative)."""
+    try:
+        from oracle.parity import RUN_LOG
+    except Exception:
+        return
+    if RUN_LOG:
+        terminalreporter.write_line(
+            "oracle parity: %d checks, %d positions, %d tie-excused (%d at the k-boundary), max_rel_err_D = %.3g"
+            % (len(RUN_LOG), sum(s["positions"] for s in RUN_LOG), sum(s["excused"] for s in RUN_LOG),
+               sum(s["boundary_swaps"] for s in RUN_LOG), max(s["max_rel_err_D"] for s in RUN_LOG)))

@@ -1,0 +1,123 @@
+"""The real multi-GPU path: one process per GPU, NCCL, NVLink peer memory (skipped on a box with fewer than 2 GPUs).
+
+ShardedIndexFlat with the bound exchange (two-phase search, batch-wise over two streams) and the exchange-fused peer
+merge must return, on every rank,
+  * exactly what ONE unsharded index returns on the same rows (bit for bit: ids and distances), and
+  * what the CPU oracle returns (oracle/parity.py rule, reference's next candidates included),
+for ragged speed-weighted shards, several add() segments, both metrics, k = 10 and k = 1000, one and several query
+batches, with and without the stream pipeline.  Mirrors /root/reference/tests/test_main.py:10-27 in spirit: known
+answers through the real path."""
+import os
+import socket
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(REPO))
+    sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import knn_b200
+    from knn_b200.distributed import ShardedIndexFlat
+    from oracle import flat_oracle as fo
+    from oracle.parity import check_parity
+
+    log = []
+    rng = np.random.default_rng(11)
+    d, n, nq = 256, 60011, 700
+    centers = rng.standard_normal((50, d)).astype(np.float32)
+    xb = (centers[rng.integers(0, 50, n)] + 0.7 * rng.standard_normal((n, d))).astype(np.float32)  # clustered: many near-equal scores
+    xb[1000:1040] = xb[3]                                    # exact duplicates: ties broken by id across shard boundaries
+    xb[n - 30:] = xb[3]
+    xq = (centers[rng.integers(0, 50, nq)] + 0.7 * rng.standard_normal((nq, d))).astype(np.float32)
+    xq[5] = xb[3]
+    weights = [0.8, 1.2] + [1.0] * (world - 2)               # ragged, speed-proportional shards
+    xb_d, xq_d = torch.from_numpy(xb).to(dev), torch.from_numpy(xq).to(dev)
+    for metric in (knn_b200.METRIC_INNER_PRODUCT, knn_b200.METRIC_L2):
+        single = knn_b200.IndexFlat(d, metric, device=rank)
+        single.set_param("path", 2)
+        single.add(xb_d)
+        for pipeline in (True, False):
+            index = ShardedIndexFlat(d, metric, device=rank, exchange_bounds=True, peer_merge=True, shard_weights=weights)
+            index.pipeline_batches = pipeline
+            index.local.set_param("path", 2)                 # tensor-core filter + bound exchange even on these small shards
+            index.local.set_param("query_batch", 256)        # 3 query batches: the batch-wise pipeline is exercised
+            index.add(xb_d[:20000])                          # three add() segments: local -> global id mapping
+            index.add(xb_d[20000:20001])
+            index.add(xb_d[20001:])
+            assert index.ntotal == n and 0 < index.local.ntotal < n
+            for k in (10, 1000):
+                D, I = index.search(xq_d, k)
+                assert int(index.local.stat("path")) == 2
+                D1, I1 = single.search(xq_d, k)
+                assert torch.equal(I, I1), (rank, metric, k, pipeline, "ids differ from the unsharded index")
+                assert torch.equal(D, D1), (rank, metric, k, pipeline, "distances differ from the unsharded index")
+                if pipeline:
+                    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric, want=k + 4)
+                    st = check_parity(D.cpu().numpy(), I.cpu().numpy(), D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-2)
+                    log.append((metric, k, st["excused"], st["max_rel_err_D"]))
+            # numpy in / numpy out goes through the same path
+            Dn, In = index.search(xq[:33], 10)
+            D1, I1 = single.search(xq_d[:33].contiguous(), 10)
+            assert np.array_equal(In, I1.cpu().numpy()) and np.array_equal(Dn, D1.cpu().numpy())
+            index.close()
+    # a larger, GEMM-shaped case: 3 default-size query batches, unit vectors at d = 1024, vs the unsharded index
+    g = torch.Generator(device=dev).manual_seed(5)
+    xb2 = torch.randn(300_000, 1024, device=dev, generator=g)
+    xq2 = torch.randn(40_000, 1024, device=dev, generator=g)
+    knn_b200.normalize_L2(xb2)
+    knn_b200.normalize_L2(xq2)
+    single = knn_b200.IndexFlat(1024, 0, device=rank)
+    single.add(xb2)
+    index = ShardedIndexFlat(1024, 0, device=rank, shard_weights=weights)
+    index.add(xb2)
+    index.profile_phases = True
+    for k in (100,):
+        D, I = index.search(xq2, k)
+        D1, I1 = single.search(xq2, k)
+        assert torch.equal(I, I1) and torch.equal(D, D1), (rank, "large case")
+    assert "exchange_finish_exposed" in index.last_phases_ms
+    index.close()
+    dist.barrier()
+    if rank == 0:
+        (Path(out_dir) / "ok").write_text(repr(log))
+    dist.destroy_process_group()
+
+
+def test_sharded_two_phase_search_over_nccl_equals_unsharded_and_oracle(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=False)
+    deadline = time.time() + 600
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("multi-GPU workers did not finish in 600 s")
+    log = (tmp_path / "ok").read_text()
+    print("oracle parity over NCCL (metric, k, excused, max_rel_err_D):", log)

@@ -182,7 +182,7 @@ def test_exact_path_parity(knn, case, metric):
     xq, xb = _data(nq, nb, d, seed=nq + nb + d, normalize=norm and metric == IP, scale=2.5)
     D, I, idx = _search(knn, xq, xb, k, metric, path=1)
     assert idx.stat("path") == 1
-    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric, want=k + 4)  # + the next candidates: k-boundary rule
     stats = check_parity(D, I, D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-3)
     assert stats["positions"] == nq * k
 
@@ -215,7 +215,7 @@ def test_tensor_path_parity(knn, case, metric, cta_group, fmt):
     assert idx.stat("path") == 2 and idx.stat("gemm_launches") >= 1
     assert idx.stat("shadow_fmt") == fmt
     assert idx.stat("overflow_batches") == 0
-    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric, want=k + 4)  # + the next candidates: k-boundary rule
     # L2 on unnormalised rows: |x|^2+|y|^2 ~ 6000, so the fp32 expansion formula resolves distances to
     # ~5e-4 only - comparable to the gaps between consecutive neighbours at k >= 1000; more positions
     # are legitimately undecidable in fp32 (still arbitrated one by one in fp64 by check_parity).
@@ -238,7 +238,7 @@ def test_tensor_path_real_embeddings(knn, golden_dir):
     fo.normalize_L2(xq)
     D, I, idx = _search(knn, xq, xb, 100, IP, path=2)
     assert idx.stat("path") == 2
-    D_ref, I_ref = fo.knn_flat(xq, xb, 100, IP)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 100, IP, want=100 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, I, D_ref, I_ref, xq, xb, IP, max_excused_frac=5e-3)
 
 
@@ -248,7 +248,7 @@ def test_exact_ties_lower_id_first(knn, path):
     xq, xb = _data(96, 4500, 128, seed=11)
     xb = np.concatenate([xb, xb])  # row j and row j + 4500 are identical
     D, I, _ = _search(knn, xq, xb, 20, IP, path=path, tensor_min_n=1)
-    D_ref, I_ref = fo.knn_flat(xq, xb, 20, IP)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 20, IP, want=20 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, I, D_ref, I_ref, xq, xb, IP, max_excused_frac=5e-3)
     pairs = I.reshape(96, 10, 2)
     assert (pairs[:, :, 1] == pairs[:, :, 0] + 4500).all()
@@ -293,7 +293,7 @@ def test_incremental_add_and_reset(knn):
     idx.add(xb[1001:])
     assert idx.ntotal == 6000
     D, I = idx.search(xq, 7)
-    D_ref, I_ref = fo.knn_flat(xq, xb, 7, IP)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 7, IP, want=7 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, I, D_ref, I_ref, xq, xb, IP)
     got = idx.reconstruct_n(998, 5)
     assert np.array_equal(got, xb[998:1003])
@@ -312,7 +312,7 @@ def test_add_copies_caller_memory(knn):
     idx.add(xb)
     xb[:] = 0
     D, I = idx.search(xq, 3)
-    D_ref, I_ref = fo.knn_flat(xq, keep, 3, IP)
+    D_ref, I_ref = fo.knn_flat(xq, keep, 3, IP, want=3 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, I, D_ref, I_ref, xq, keep, IP)
 
 
@@ -321,13 +321,13 @@ def test_input_coercion_like_faiss(knn):
     idx = knn.IndexFlat(48, L2)
     idx.add(xb.astype(np.float64))            # dtype coerced
     D, I = idx.search(np.asfortranarray(xq), 4)  # layout coerced
-    D_ref, I_ref = fo.knn_flat(xq, xb, 4, L2)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 4, L2, want=4 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, I, D_ref, I_ref, xq, xb, L2)
     fp16 = xb.astype(np.float16)               # cath/search.py:40 up-casts fp16 files
     idx2 = knn.IndexFlat(48, L2)
     idx2.add(fp16.astype(np.float32))
     D, I = idx2.search(xq, 4)
-    D_ref, I_ref = fo.knn_flat(xq, fp16.astype(np.float32), 4, L2)
+    D_ref, I_ref = fo.knn_flat(xq, fp16.astype(np.float32), 4, L2, want=4 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, I, D_ref, I_ref, xq, fp16.astype(np.float32), L2)
 
 
@@ -361,7 +361,7 @@ def test_bf16_storage_index(knn):
         idx.set_param("path", path)
         idx.add(xb)
         D, I = idx.search(xq, 50)
-        D_ref, I_ref = fo.knn_flat(xq, xb_r, 50, IP)
+        D_ref, I_ref = fo.knn_flat(xq, xb_r, 50, IP, want=50 + 4)  # + the next candidates: k-boundary rule
         check_parity(D, I, D_ref, I_ref, xq, xb_r, IP, max_excused_frac=2e-3)
 
 
@@ -379,7 +379,7 @@ def test_few_queries_stream_kernel(knn, nq, nb, d, k, metric):
             D, I, idx = _search(knn, xq, xb, k, metric, path=2, shadow_fmt=fmt, stream_kernel=stream)
             assert idx.stat("path") == 2 and idx.stat("overflow_batches") == 0
             assert np.array_equal(I, I1) and np.array_equal(D, D1), (fmt, stream)
-    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric, want=k + 4)  # + the next candidates: k-boundary rule
     check_parity(D1, I1, D_ref, I_ref, xq, xb, metric, max_excused_frac=2e-3 if metric == IP else 1e-2)
 
 
@@ -411,7 +411,7 @@ def test_shadow_format_is_chosen_from_the_data(knn):
     idx.search(xq, 5)
     assert idx.stat("shadow_conversions") == 1  # stays bf16
     all_rows = np.concatenate([xb, big])
-    D_ref, I_ref = fo.knn_flat(xq, all_rows, 5, L2)
+    D_ref, I_ref = fo.knn_flat(xq, all_rows, 5, L2, want=5 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, I, D_ref, I_ref, xq, all_rows, L2, max_excused_frac=1e-2)
     idx.reset()
     idx.add(xb)
@@ -434,7 +434,7 @@ def test_shadow_format_switch_and_forced_fp16_out_of_range(knn):
         assert idx.stat("shadow_fmt") == fmt
     assert idx.stat("shadow_conversions") == 2
     assert np.array_equal(res[FP16][1], res[BF16][1]) and np.array_equal(res[FP16][0], res[BF16][0])
-    D_ref, I_ref = fo.knn_flat(xq, xb, 30, IP)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 30, IP, want=30 + 4)  # + the next candidates: k-boundary rule
     check_parity(res[FP16][0], res[FP16][1], D_ref, I_ref, xq, xb, IP, max_excused_frac=2e-3)
     xq, xb = _data(64, 9000, 64, seed=24, normalize=False, scale=3e5)
     D, I, idx = _search(knn, xq, xb, 7, IP, path=2, shadow_fmt=FP16)
@@ -488,7 +488,7 @@ def test_bf16_operands_with_fewer_mantissa_bits(knn, bits):
         res[path] = idx.search(xq, 20)
     assert np.array_equal(res[1][1], res[2][1]) and np.array_equal(res[1][0], res[2][0])
     xb_r = torch.from_numpy(xb).to(torch.bfloat16).to(torch.float32).numpy()
-    D_ref, I_ref = fo.knn_flat(xq, xb_r, 20, L2)
+    D_ref, I_ref = fo.knn_flat(xq, xb_r, 20, L2, want=20 + 4)  # + the next candidates: k-boundary rule
     check_parity(res[2][0], res[2][1], D_ref, I_ref, xq, xb_r, L2, max_excused_frac=2e-3)
 
 
@@ -503,7 +503,7 @@ def test_nan_rows_never_enter_a_result(knn, path, fmt):
     xb_nan[bad, 5] = np.nan
     D, I, _ = _search(knn, xq, xb_nan, 25, IP, path=path, shadow_fmt=fmt)
     keep = np.setdiff1d(np.arange(12000), bad)
-    D_ref, I_ref = fo.knn_flat(xq, xb[keep], 25, IP)
+    D_ref, I_ref = fo.knn_flat(xq, xb[keep], 25, IP, want=25 + 4)  # + the next candidates: k-boundary rule
     check_parity(D, keep_inverse(I, keep), D_ref, I_ref, xq, xb[keep], IP, max_excused_frac=2e-3)
     assert not np.isin(I, bad).any() and np.isfinite(D).all()
 
@@ -546,7 +546,7 @@ def test_torch_device_api_and_merge(knn):
     full.add(tb)
     D, I = full.search(tq, 30)
     assert D.is_cuda and I.dtype == torch.int64
-    D_ref, I_ref = fo.knn_flat(xq, xb, 30, IP)
+    D_ref, I_ref = fo.knn_flat(xq, xb, 30, IP, want=30 + 4)  # + the next candidates: k-boundary rule
     check_parity(D.cpu().numpy(), I.cpu().numpy(), D_ref, I_ref, xq, xb, IP, max_excused_frac=2e-3)
     # row-sharded: 3 ragged shards, global ids via id_base, merged on the device
     bounds = [0, 7000, 15001, 24000]
@@ -588,7 +588,7 @@ def test_properties_at_scale(knn):
     assert all(len(set(r)) == 100 for r in In[::64].tolist())
     sample = np.arange(0, 8192, 128)
     xb_h = xb.cpu().numpy()
-    D_ref, I_ref = fo.knn_flat(xb_h[sample], xb_h, 100, IP)
+    D_ref, I_ref = fo.knn_flat(xb_h[sample], xb_h, 100, IP, want=100 + 4)  # + the next candidates: k-boundary rule
     check_parity(Dn[sample], In[sample], D_ref, I_ref, xb_h[sample], xb_h, IP, max_excused_frac=5e-3)
 
 
@@ -628,7 +628,7 @@ def test_two_phase_sharded_search_equals_single_index(knn, metric, normalize):
     Ds, Is = zip(*[sh.search_finish(lower, k, id_base=a) for sh, a in zip(shards, bounds[:-1])])
     Dm, Im = knn.merge_topk(torch.stack(Ds), torch.stack(Is), metric)
     assert torch.equal(Im, I) and torch.equal(Dm, D)
-    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric)
+    D_ref, I_ref = fo.knn_flat(xq, xb, k, metric, want=k + 4)  # + the next candidates: k-boundary rule
     check_parity(Dm.cpu().numpy(), Im.cpu().numpy(), D_ref, I_ref, xq, xb, metric, max_excused_frac=1e-2)
     # a shard on the exact path takes part too (its bound is -FLT_MAX)
     small = knn.IndexFlat(256, metric)

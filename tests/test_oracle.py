@@ -168,3 +168,73 @@ def test_parity_checker_excuses_only_fp32_near_ties():
         check_parity(Dp, I_nopad, Dp, Ip, xq, xb[:2], 0)
     with pytest.raises(ParityError):
         check_parity(D.astype(np.float64), I, D, I, xq, xb, 0)
+
+
+def test_parity_checker_distance_bound_is_the_stated_1e5_relative():
+    """BASELINE.json: 'distances must agree within 1e-5 relative' - no additive slack for scores away from zero;
+    only scores within 100 tau of zero fall back to the absolute tie tolerance."""
+    rng = np.random.default_rng(5)
+    xb = rng.standard_normal((400, 1024)).astype(np.float32)
+    xq = rng.standard_normal((3, 1024)).astype(np.float32)
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    D, I = fo.knn_flat(xq, xb, 6, 0)
+    assert D.min() > 100 * 2 * 32 * 2.0 ** -24  # every score is in the relative regime
+    ok = D * np.float32(1 + 5e-6)
+    assert check_parity(ok, I, D, I, xq, xb, 0)["max_rel_err_D"] == pytest.approx(5e-6, rel=0.2)
+    # 4e-5 relative passed the old checker at this magnitude (its additive tau term); the stated bar rejects it
+    with pytest.raises(ParityError, match="relative 1e-5"):
+        check_parity(D * np.float32(1 + 4e-5), I, D, I, xq, xb, 0)
+    # a score next to zero: relative error is meaningless there, the absolute tolerance applies
+    xb0 = xb.copy()
+    xb0[I[0, 0]] -= xq[0] * (xb0[I[0, 0]] @ xq[0])  # orthogonal to query 0: score ~ 1e-9
+    D0, I0 = fo.knn_flat(xq[:1], xb0[I[0, :1]], 1, 0)
+    assert abs(D0[0, 0]) < 1e-6
+    check_parity(D0 + np.float32(1e-7), I0, D0, I0, xq[:1], xb0[I[0, :1]], 0)
+    with pytest.raises(ParityError, match="near-zero"):
+        check_parity(D0 + np.float32(1e-5), I0, D0, I0, xq[:1], xb0[I[0, :1]], 0)
+
+
+def _near_tie_rows(base, n, rng, rel=1e-7):
+    """n copies of `base` whose scores against any query differ by ~rel (far below tau, above fp32 resolution of the sum)."""
+    rows = np.repeat(base[None], n, 0).copy()
+    for i in range(n):
+        rows[i, i] = rows[i, i] * np.float32(1 + rel * (i + 1) * 8)
+    return rows
+
+
+def test_parity_checker_k_boundary_and_cluster_rules():
+    """inside a tau-cluster the id multiset must match; the cluster at the k-boundary may trade
+    members with the reference's (k+1)-th candidate when that lies inside tau - and only then."""
+    rng = np.random.default_rng(6)
+    d = 64
+    xb = rng.standard_normal((40, d)).astype(np.float32)
+    xq = rng.standard_normal((1, d)).astype(np.float32)
+    xq[0] = xb[5] * 3  # row 5 is the clear best hit
+    xb[20:23] = _near_tie_rows(xb[5] * np.float32(0.9), 3, rng)  # a cluster of three near-identical rows right behind the best hit
+    D_ref, I_ref = fo.knn_flat(xq, xb, 8, 0)
+    row = I_ref[0].tolist()
+    cl = [row.index(i) for i in (20, 21, 22)]
+    assert max(cl) - min(cl) == 2, "the three near-ties sit next to each other"
+    # k chosen so that the boundary cuts the cluster: two members inside, the third is the (k+1)-th candidate
+    k = min(cl) + 2
+    D, I = D_ref[:, :k].copy(), I_ref[:, :k].copy()
+    I[0, k - 1], D[0, k - 1] = I_ref[0, k], D_ref[0, k]  # took the (k+1)-th instead of the k-th: a valid fp32 answer
+    stats = check_parity(D, I, D_ref[:, :k + 1], I_ref[:, :k + 1], xq, xb, 0)
+    assert stats["boundary_swaps"] == 1 and stats["excused"] == 1
+    # the same swap with a row that is NOT inside tau of the boundary is a real error
+    far = [i for i in range(40) if i not in row][0]
+    I_bad = I_ref[:, :k].copy()
+    I_bad[0, k - 1] = far
+    with pytest.raises(ParityError):
+        check_parity(D_ref[:, :k].copy(), I_bad, D_ref[:, :k + 1], I_ref[:, :k + 1], xq, xb, 0)
+    # permutation inside the cluster (away from the boundary): excused, multiset unchanged
+    kk = max(cl) + 2
+    I_perm = I_ref[:, :kk].copy()
+    I_perm[0, cl[0]], I_perm[0, cl[2]] = I_ref[0, cl[2]], I_ref[0, cl[0]]
+    assert check_parity(D_ref[:, :kk].copy(), I_perm, D_ref[:, :kk + 1], I_ref[:, :kk + 1], xq, xb, 0)["excused"] == 2
+    # an id from outside replacing a cluster member in the middle of the row: multiset violated
+    I_out = I_ref[:, :kk].copy()
+    I_out[0, cl[1]] = far
+    with pytest.raises(ParityError):
+        check_parity(D_ref[:, :kk].copy(), I_out, D_ref[:, :kk + 1], I_ref[:, :kk + 1], xq, xb, 0)

@@ -208,3 +208,32 @@ def test_drivers_search_and_save_and_proteins_search(tmp_path):
     assert again.ntotal == 3000
     with pytest.raises(ValueError):
         drivers.proteins_search(tmp_path / "pfam", "hnsw")
+
+
+@pytest.mark.gpu
+def test_create_index_flat_then_search_and_check_auc1(golden_dir, tmp_path, expected):
+    """/root/reference/tests/test_utils.py:17-22 (`create_index.main(["--dir", ..., "--index", ...])`, file exists) plus
+    the "Search and check AUC1" the reference left as a TODO: the file is loaded the way seqvec_search/main.py:131-132
+    does (`read_index`), handed to `faiss_search` as a ready index, and must reproduce the known answers of
+    tests/test_main.py:26-27 (0.871 / 0.91) - identical to searching `train.npy` directly."""
+    import knn_b200
+    from knn_b200 import drivers
+    from oracle.evaluate import Fixture
+
+    fx = Fixture(golden_dir / "pfam-20-10")
+    out = tmp_path / "index.bin"
+    drivers.create_index(["--dir", str(golden_dir / "pfam-20-10"), "--index", str(out)])
+    assert out.exists()
+    assert out.read_bytes()[:4] == b"IxFI" and out.stat().st_size == 45 + 200 * 1024 * 4
+    knn_index = knn_b200.read_index(str(out))
+    assert (knn_index.ntotal, knn_index.d, knn_index.metric_type) == (200, 1024, 0)
+    results, scores, _ = drivers.faiss_search(knn_index, np.load(fx.test), 10)
+    auc1s, tps = knn_b200.evaluate_faiss(fx, results)
+    assert np.mean(auc1s) == 0.871 and np.mean(tps) == 0.91
+    assert np.array_equal(results, expected["pfam-20-10.ip.k10.I"])
+    direct, direct_scores, _ = drivers.faiss_search(np.load(fx.train), np.load(fx.test), 10)
+    assert np.array_equal(results, direct) and np.array_equal(scores, direct_scores)
+    with pytest.raises(NotImplementedError, match="exact"):
+        drivers.create_index(["--dir", str(golden_dir / "pfam-20-10"), "--index", str(out), "--kind", "lsh"])
+    with pytest.raises(NotImplementedError, match="exact"):
+        knn_b200.IndexLSH(1024, 1024)

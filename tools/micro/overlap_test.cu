@@ -30,9 +30,11 @@ int main() {
     cudaEventCreate(&ea0); cudaEventCreate(&ea1); cudaEventCreate(&eb0); cudaEventCreate(&eb1);
     for (int cluster = 1; cluster <= 2; ++cluster) {
         for (int big_smem : {165136, 100000, 220000}) {
-            for (int small_smem : {0, 4096, 34320}) {
+            for (int small_smem : {0, 4096, 34320})
+            for (int carve : {-1, 100}) {  // preferred shared-memory carveout of the small kernel: driver default / max shared
                 cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, 230000);
                 cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+                cudaFuncSetAttribute(small_k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(148); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = big_smem; cfg.stream = a;
                 cudaLaunchAttribute at[1];
@@ -51,8 +53,8 @@ int main() {
                 cudaEventElapsedTime(&big_ms, ea0, ea1);
                 cudaEventElapsedTime(&small_end_ms, ea0, eb1);
                 cudaEventElapsedTime(&small_ms, eb0, eb1);
-                printf("cluster=%d big_smem=%d small_smem=%d: big %.3f ms, small finished at %.3f ms (took %.3f) -> %s  [%s]\n", cluster,
-                       big_smem, small_smem, big_ms, small_end_ms, small_ms, small_end_ms < big_ms * 0.9 ? "OVERLAPPED" : "serialized",
+                printf("cluster=%d big_smem=%d small_smem=%d carveout=%d: big %.3f ms, small finished at %.3f ms (took %.3f) -> %s  [%s]\n", cluster,
+                       big_smem, small_smem, carve, big_ms, small_end_ms, small_ms, small_end_ms < big_ms * 0.9 ? "OVERLAPPED" : "serialized",
                        cudaGetErrorString(cudaGetLastError()));
             }
         }
