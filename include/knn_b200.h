@@ -147,6 +147,19 @@ int knn_merge_topk_peer_dev(int metric, int64_t nq, int64_t k, int nranks, int64
                             const void* const* D_peer, const void* const* I_peer, void* const* D_out_peer,
                             void* const* I_out_peer, void* stream);
 
+/* Bound exchange of the two-phase search over the same peer memory, so that it can run per query batch on a side
+ * stream next to the GEMM of the following batch (an NCCL kernel does not fit next to a resident GEMM CTA).
+ * push:     stores src_dev[0..n) into slot [rank] of EVERY rank's slot array (slots_peer[l] = address of rank l's
+ *           float array [nranks][n] as mapped on this device) and then raises flags_peer[l][rank] to `epoch`
+ *           (release, system scope).  counter_dev: one zero-initialised uint32 of scratch on this device.
+ * wait_max: waits until all `nranks` local flags have reached `epoch` (acquire, system scope; gives up after ~4 s and
+ *           sets *timeout_flag_dev instead of hanging), then out_dev[i] = max over ranks of slots_dev[r][i].
+ * Epochs increase from call to call; the caller separates two uses of the same slots by a barrier (the result merge). */
+int knn_bounds_push_peer_dev(int nranks, int rank, int64_t n, const float* src_dev, void* const* slots_peer,
+                             void* const* flags_peer, uint32_t epoch, uint32_t* counter_dev, void* stream);
+int knn_bounds_wait_max_dev(int nranks, int64_t n, const float* slots_dev, const uint32_t* flags_dev, uint32_t epoch,
+                            float* out_dev, int* timeout_flag_dev, void* stream);
+
 /* ---- Downstream of search: what the reference does with (D, I) next. ----
  * All pointers are device pointers; I is the (nq,k) int64 matrix index.search returned, D its float32 scores.
  * Label gathers keep Python/numpy index semantics: a negative id counts from the end (id -1 -> last row).

@@ -550,9 +550,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // a handful of queries; here a launch is a pure stream of the 16-bit rows: the bandwidth kernel of the path.
 // Accumulator: 128 TMEM lanes = database rows, NQT columns = queries; an epilogue thread owns one database row and
 // compares its NQT scores with the per-query thresholds (shared memory).
-constexpr int SBM = 128;            // database rows per tile
+constexpr int SBM = 128;            // database rows per CTA and tile
 constexpr int kStreamAcc = 4;       // accumulator stages of NQT columns
-constexpr int kStreamTmemCols = 256;
 constexpr int kStreamMaxStages = 10;
 constexpr uint32_t kStreamBytesA = SBM * BK * 2;
 
@@ -565,26 +564,38 @@ struct StreamBarriers {
     uint32_t tmem_base;
 };
 
-static size_t stream_smem_bytes(int nqt, int num_kb, int stages) {
-    return 1024 /*align slack*/ + size_t(num_kb) * nqt * BK * 2 + size_t(stages) * kStreamBytesA + sizeof(StreamBarriers) + 64 * sizeof(float) + 64;
+// nq_cta: query rows resident per CTA (NQT for one CTA, NQT / 2 for a CTA pair)
+static size_t stream_smem_bytes(int nq_cta, int num_kb, int stages) {
+    return 1024 /*align slack*/ + size_t(num_kb) * nq_cta * BK * 2 + size_t(stages) * kStreamBytesA + sizeof(StreamBarriers) + 128 * sizeof(float) + 64;
 }
 
-template <int NQT, bool L2, bool DENSE>
+// CG = 2 (NQT = 128): a CTA pair works on 256 database rows with tcgen05.mma.cta_group::2 (M = 256, N = 128).  Each
+// CTA streams ITS 128 rows and keeps HALF of the queries resident (64 rows = 128 KB at d = 1024, what one CTA holds
+// for NQT = 64): the pair's tensor cores read both halves of the N operand, so 128 queries cost no more shared memory
+// per SM than 64 - and the launch stays a pure stream of database bytes where the main kernel would pad the batch to
+// a 256-query tile pair and re-load the query tile with every stage.
+template <int NQT, bool L2, bool DENSE, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
+    constexpr int NQ_CTA = NQT / CG;                 // query rows staged by one CTA
+    constexpr uint32_t kTmemColsS = NQT * kStreamAcc < 32 ? 32 : NQT * kStreamAcc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int nstages = args.stages;
-    const uint32_t bytes_q_kb = NQT * BK * 2;                       // one K block of the resident queries
-    uint8_t* smem_q = smem;                                         // [num_kb][NQT x 64] 128-byte swizzled
+    const uint32_t bytes_q_kb = NQ_CTA * BK * 2;                    // one K block of this CTA's resident queries
+    uint8_t* smem_q = smem;                                         // [num_kb][NQ_CTA x 64] 128-byte swizzled
     uint8_t* smem_a = smem + size_t(args.num_kb) * bytes_q_kb;      // [nstages][128 x 64]
     StreamBarriers* bars = reinterpret_cast<StreamBarriers*>(smem_a + size_t(nstages) * kStreamBytesA);
     float* thr_s = reinterpret_cast<float*>(bars + 1);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = args.n_tiles;  // tiles of 128 database rows
-    // instruction descriptor: M = 128, N = NQT
-    const uint32_t idesc = (args.idesc & ~((0x3Fu << 17) | (0x1Fu << 24))) | (uint32_t(NQT >> 3) << 17) | (uint32_t(SBM >> 4) << 24);
+    const int num_tiles = args.n_tiles;  // tiles of 128 * CG database rows
+    const uint32_t cta_rank = CG == 1 ? 0u : cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int unit = CG == 1 ? blockIdx.x : (blockIdx.x >> 1);
+    const int num_units = CG == 1 ? gridDim.x : (gridDim.x >> 1);
+    // instruction descriptor: M = 128 * CG, N = NQT
+    const uint32_t idesc = (args.idesc & ~((0x3Fu << 17) | (0x1Fu << 24))) | (uint32_t(NQT >> 3) << 17) | (uint32_t((SBM * CG) >> 4) << 24);
 
     if (warp == kProducerWarp && lane == 0) {
         prefetch_tmap(&map_q);
@@ -595,44 +606,56 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         for (int i = 0; i < kStreamAcc; ++i) {
             mbar_init(&bars->acc_full[i], 1);
-            mbar_init(&bars->acc_empty[i], 4);
+            mbar_init(&bars->acc_empty[i], 4 * CG);
         }
         mbar_init(&bars->queries, 1);
         fence_barrier_init();
     }
-    if (warp == kMmaWarp) tmem_alloc<1>(&bars->tmem_base, kStreamTmemCols);
-    if (threadIdx.x < 64) thr_s[threadIdx.x] = (threadIdx.x < NQT && threadIdx.x < args.nq) ? args.thr[threadIdx.x] : FLT_MAX;
+    if (warp == kMmaWarp) tmem_alloc<CG>(&bars->tmem_base, kTmemColsS);
+    if (threadIdx.x < 128) thr_s[threadIdx.x] = (threadIdx.x < NQT && threadIdx.x < args.nq) ? args.thr[threadIdx.x] : FLT_MAX;
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == kProducerWarp) {
         if (lane == 0) {
-            mbar_expect_tx(&bars->queries, uint32_t(args.num_kb) * bytes_q_kb);
-            for (int kb = 0; kb < args.num_kb; ++kb)
-                tma_load_2d(smem_q + size_t(kb) * bytes_q_kb, &map_q, &bars->queries, kb * BK, 0, args.hint_q);
+            // resident queries: this CTA's share of the N operand
+            if constexpr (CG == 1) {
+                mbar_expect_tx(&bars->queries, uint32_t(args.num_kb) * bytes_q_kb);
+                for (int kb = 0; kb < args.num_kb; ++kb)
+                    tma_load_2d(smem_q + size_t(kb) * bytes_q_kb, &map_q, &bars->queries, kb * BK, 0, args.hint_q);
+            } else {
+                if (leader) mbar_expect_tx(&bars->queries, uint32_t(args.num_kb) * bytes_q_kb * 2);
+                for (int kb = 0; kb < args.num_kb; ++kb)
+                    tma_load_2d_pair(smem_q + size_t(kb) * bytes_q_kb, &map_q, &bars->queries, kb * BK, int(cta_rank) * NQ_CTA, args.hint_q);
+            }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int row_db = int(args.j0) + tile * SBM;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                const int row_db = int(args.j0) + tile * (SBM * CG) + int(cta_rank) * SBM;
                 for (int kb = 0; kb < args.num_kb; ++kb) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    mbar_expect_tx(&bars->full[stage], kStreamBytesA);
-                    tma_load_2d(smem_a + size_t(stage) * kStreamBytesA, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
+                    if constexpr (CG == 1) {
+                        mbar_expect_tx(&bars->full[stage], kStreamBytesA);
+                        tma_load_2d(smem_a + size_t(stage) * kStreamBytesA, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
+                    } else {
+                        if (leader) mbar_expect_tx(&bars->full[stage], kStreamBytesA * 2);
+                        tma_load_2d_pair(smem_a + size_t(stage) * kStreamBytesA, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
+                    }
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             mbar_wait(&bars->queries, 0);
             tc_fence_after();
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + uint32_t(acc * NQT);
@@ -643,21 +666,21 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     const uint64_t db = make_smem_desc(smem_u32(smem_q + size_t(kb) * bytes_q_kb));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_f16<1>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit<1>(&bars->empty[stage]);
+                        umma_f16<CG>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit<CG>(&bars->empty[stage]);
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit<1>(&bars->acc_full[acc]);
+                umma_commit<CG>(&bars->acc_full[acc]);
                 if (++acc == kStreamAcc) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ===== epilogue: warp w owns database rows 32 w .. 32 w + 31 of the tile (TMEM lanes) =====
+        // ===== epilogue: warp w owns database rows 32 w .. 32 w + 31 of this CTA's half of the tile (TMEM lanes) =====
         int acc = 0;
         uint32_t acc_phase = 0;
         const int nq = int(args.nq < NQT ? args.nq : NQT);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int64_t j = args.j0 + int64_t(tile) * SBM + warp * 32 + lane;  // this thread's database row
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
+            const int64_t j = args.j0 + int64_t(tile) * (SBM * CG) + int64_t(cta_rank) * SBM + warp * 32 + lane;  // this thread's database row
             const bool row_ok = j < args.j1;
             float yn = 0.f;
             if (L2 && row_ok) yn = __ldg(args.ynorm2 + j);
@@ -708,16 +731,19 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+            if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(&bars->acc_empty[acc]);
+                else mbar_arrive_remote(&bars->acc_empty[acc], 0);
+            }
             if (++acc == kStreamAcc) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc<1>(tmem_base, kStreamTmemCols);
+        tmem_dealloc<CG>(tmem_base, kTmemColsS);
     }
 }
 
@@ -735,7 +761,8 @@ struct GemmPlan {
     int debug_skip_epilogue = 0;
     int stages = 0;     // 0: default depth (4)
     int stream_kernel = 1;  // launches with <= 64 queries use the few-queries variant (database rows as the M operand)
-    int small_m128 = 1;     // launches with 65..128 queries use the single-CTA (M = 128) variant of the main kernel
+    int stream_pair = 1;    // launches with 65..128 queries use the CTA-pair form of the few-queries variant
+    int small_m128 = 0;     // experiments: launches with 65..128 queries use the single-CTA (M = 128) variant of the main kernel
 };
 
 void gemm_plan_set_cta_group(GemmPlan* p, int cg) { p->cta_group = cg == 1 ? 1 : 2; }
@@ -744,6 +771,7 @@ void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue) { p->debug_skip_epilogu
 void gemm_plan_set_stages(GemmPlan* p, int stages) { p->stages = stages; }
 void gemm_plan_set_stream_kernel(GemmPlan* p, int on) { p->stream_kernel = on; }
 void gemm_plan_set_small_m128(GemmPlan* p, int on) { p->small_m128 = on; }
+void gemm_plan_set_stream_pair(GemmPlan* p, int on) { p->stream_pair = on; }
 int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
@@ -797,6 +825,12 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             int(Cfg<CG>::smem_bytes(CG == 1 ? 4 : kMaxStages))));
+        // The SM's shared-memory carveout is picked from a few sizes when the (persistent) CTA lands and cannot change
+        // while it is resident: with the default the 162 KB of the 4-stage ring select the 164 KB configuration and
+        // nothing else that uses shared memory fits next to it (tools/micro/overlap_test.cu).  Asking for the largest
+        // carveout leaves ~64 KB for the rescoring / selection kernels of the previous query batch, which run on a
+        // side stream under this kernel (index.cu: search_tensor).
+        KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const int64_t tiles = int64_t(a.m_tiles) * a.n_tiles;
@@ -819,10 +853,10 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     return KNN_OK;
 }
 
-template <int NQT, bool L2, bool DENSE>
+template <int NQT, bool L2, bool DENSE, int CG>
 static int launch_stream_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorMap& map_db, const GemmArgs& a, size_t smem,
                                  cudaStream_t s) {
-    auto kern = gemm_stream_kernel<NQT, L2, DENSE>;
+    auto kern = gemm_stream_kernel<NQT, L2, DENSE, CG>;
     static bool attr_done[64] = {};
     int dev = 0;
     KNN_CHECK_CUDA(cudaGetDevice(&dev));
@@ -830,8 +864,21 @@ static int launch_stream_variant(GemmPlan* p, const CUtensorMap& map_q, const CU
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    const int grid = a.n_tiles < p->sms ? a.n_tiles : p->sms;
-    kern<<<grid, kThreads, smem, s>>>(map_q, map_db, a);
+    const int units_max = p->sms / CG;
+    const int units = a.n_tiles < units_max ? a.n_tiles : units_max;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(units * CG), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_q, map_db, a));
     KNN_CHECK_LAUNCH();
     return KNN_OK;
 }
@@ -841,19 +888,22 @@ static int try_stream_launch(GemmPlan* p, const h16_t* xq_h16, int fmt, int64_t 
                              int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1, int metric, bool dense_first,
                              FilterState st, cudaStream_t s, bool* done) {
     *done = false;
-    if (!p->stream_kernel || nq > 64 || nq_pad < 64 || dp % BK != 0) return KNN_OK;
-    const int nqt = nq <= 32 ? 32 : 64;
+    if (!p->stream_kernel || nq > 128 || nq_pad < 128 || dp % BK != 0) return KNN_OK;
+    if (nq > 64 && !p->stream_pair) return KNN_OK;
+    const int nqt = nq <= 32 ? 32 : (nq <= 64 ? 64 : 128);
+    const int cg = nqt == 128 ? 2 : 1;  // 128 queries: a CTA pair, each CTA keeps 64 of them resident
+    const int nq_cta = nqt / cg;
     const int num_kb = dp / BK;
     int stages = kStreamMaxStages;
-    while (stages >= 4 && stream_smem_bytes(nqt, num_kb, stages) > size_t(227 * 1024)) --stages;
+    while (stages >= 4 && stream_smem_bytes(nq_cta, num_kb, stages) > size_t(227 * 1024)) --stages;
     if (stages < 4) return KNN_OK;  // the resident queries leave no room for a ring: the main kernel takes it
     CUtensorMap map_q, map_db;
-    KNN_CHECK(make_map(p, &map_q, xq_h16, nq_pad, dp, nqt));
+    KNN_CHECK(make_map(p, &map_q, xq_h16, nq_pad, dp, nq_cta));
     KNN_CHECK(make_map(p, &map_db, xb_h16, ntotal, dp, SBM));
     GemmArgs a;
     a.nq = nq;
     a.m_tiles = 1;
-    a.n_tiles = int((j1 - j0 + SBM - 1) / SBM);
+    a.n_tiles = int((j1 - j0 + SBM * cg - 1) / (SBM * cg));
     a.num_kb = num_kb;
     a.j0 = j0;
     a.j1 = j1;
@@ -868,18 +918,18 @@ static int try_stream_launch(GemmPlan* p, const h16_t* xq_h16, int fmt, int64_t 
     a.stages = stages;
     a.hint_q = kEvictNormal;
     a.hint_db = kEvictNormal;
-    const size_t smem = stream_smem_bytes(nqt, num_kb, stages);
+    const size_t smem = stream_smem_bytes(nq_cta, num_kb, stages);
     const bool l2 = metric == KNN_METRIC_L2;
     *done = true;
-#define KNN_STREAM_DISPATCH(NQTV)                                                                                     \
+#define KNN_STREAM_DISPATCH(NQTV, CGV)                                                                                \
     if (l2) {                                                                                                          \
-        return dense_first ? launch_stream_variant<NQTV, true, true>(p, map_q, map_db, a, smem, s)                     \
-                           : launch_stream_variant<NQTV, true, false>(p, map_q, map_db, a, smem, s);                   \
+        return dense_first ? launch_stream_variant<NQTV, true, true, CGV>(p, map_q, map_db, a, smem, s)                \
+                           : launch_stream_variant<NQTV, true, false, CGV>(p, map_q, map_db, a, smem, s);              \
     } else {                                                                                                           \
-        return dense_first ? launch_stream_variant<NQTV, false, true>(p, map_q, map_db, a, smem, s)                    \
-                           : launch_stream_variant<NQTV, false, false>(p, map_q, map_db, a, smem, s);                  \
+        return dense_first ? launch_stream_variant<NQTV, false, true, CGV>(p, map_q, map_db, a, smem, s)               \
+                           : launch_stream_variant<NQTV, false, false, CGV>(p, map_q, map_db, a, smem, s);             \
     }
-    if (nqt == 32) { KNN_STREAM_DISPATCH(32) } else { KNN_STREAM_DISPATCH(64) }
+    if (nqt == 32) { KNN_STREAM_DISPATCH(32, 1) } else if (nqt == 64) { KNN_STREAM_DISPATCH(64, 1) } else { KNN_STREAM_DISPATCH(128, 2) }
 #undef KNN_STREAM_DISPATCH
 }
 
@@ -887,9 +937,8 @@ int gemm_filter_launch(GemmPlan* p, const h16_t* xq_h16, int fmt_q, int64_t nq, 
                        const h16_t* xb_h16, int fmt_db, int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1,
                        int metric, bool dense_first, FilterState st, cudaStream_t s) {
     if (j1 <= j0 || nq <= 0) return KNN_OK;
-    // 65..128 queries: one CTA per tile (M = 128).  A CTA pair would pad them to M = 256 and spend twice the MMA time
-    // per database byte - at 256 queries tensor time and HBM time of a pass are equal (2 * 256 * d flop per 2 * d bytes
-    // = the machine balance), so the padded launch is tensor-bound where this one streams.
+    // small_m128 (experiments, off): 65..128 queries on single-CTA tiles (M = 128) instead of padding them to a CTA
+    // pair's M = 256.  Measured slower (4 stages of 48 KB cover less latency than the pair's 6 x 32 KB).
     const int cg = (p->cta_group == 2 && nq <= BM && p->small_m128) ? 1 : p->cta_group;
     if (dp % BK != 0 || nq_pad % (BM * cg) != 0) {
         set_error("gemm_filter: dp (%d) must be a multiple of %d and nq_pad (%lld) of %d", dp, BK, (long long)nq_pad, BM * cg);

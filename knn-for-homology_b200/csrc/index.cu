@@ -18,6 +18,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -86,6 +87,27 @@ struct PinBuf {  // page-locked host memory (bounce buffers of the host-pointer 
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// Staging copies between pageable caller memory and the pinned bounce buffers run on the calling thread while the
+// GPU works; one core moves ~8-10 GB/s, so large blocks are split over a few threads.
+inline void host_copy(void* dst, const void* src, size_t bytes) {
+    const size_t kMin = size_t(8) << 20;
+    unsigned nt = unsigned(std::min<size_t>(4, bytes / kMin));
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 4095) & ~size_t(4095);
+    for (unsigned t = 1; t < nt; ++t) {
+        const size_t off = size_t(t) * per;
+        if (off >= bytes) break;
+        const size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto& t : th) t.join();
+}
+
 // true when the driver can DMA straight to / from p (cudaHostAlloc / cudaHostRegister memory)
 inline bool host_pointer_is_pinned(const void* p) {
     cudaPointerAttributes a;
@@ -127,6 +149,7 @@ struct knn_index {
     DevBuf stage2;                      // second ingest staging buffer (knn_index_add double-buffers the H2D copies)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t hp_in_ready[2] = {nullptr, nullptr}, hp_out_done[2] = {nullptr, nullptr}, hp_computed[2] = {nullptr, nullptr};
+    cudaEvent_t hp_in_free[2] = {nullptr, nullptr};
     cudaEvent_t stage_free[2] = {nullptr, nullptr};
     // tensor path: per-query state of the filter (queries, thresholds, candidate lists)
     struct TensorWs {
@@ -134,10 +157,13 @@ struct knn_index {
     };
     TensorWs ws1[2];  // one query batch each (single-call search): batch b filters in ws1[b & 1] while batch b - 1 finishes
     TensorWs ws2;     // all queries of a two-phase search (filter ... exchange ... finish)
-    cudaStream_t side = nullptr;                  // finish phase of batch b runs here, under the GEMM of batch b + 1
+    cudaStream_t side = nullptr;                  // finish phase of batch b runs here, under the GEMM of batch b + 1 (lowest priority)
+    cudaStream_t hi = nullptr;                    // filter phase of an overlapped search (highest priority, see search_tensor)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_filtered[2] = {nullptr, nullptr};  // filter of the batch in ws1[i] done (main stream)
     cudaEvent_t ev_finished[2] = {nullptr, nullptr};  // finish of the batch in ws1[i] done (side stream): ws1[i] reusable
     int overlap_finish = 1;
+    int split_single_batch = 1;
     struct Pending {
         bool active = false, tensor = false;
         int64_t nq = 0, qb = 0, nbatches = 0;
@@ -155,7 +181,8 @@ struct knn_index {
     int debug_skip_epilogue = 0;
     int gemm_stages = 0;
     int stream_kernel = 1;
-    int small_m128 = 1;
+    int stream_pair = 1;
+    int small_m128 = 0;  // measured slower than the CTA-pair tiles (5.9 vs 4.6 ms at 128 queries x 10M rows): off
     int panel_ratio = 0;  // 0: automatic
     int64_t small_batch_nq = 256;  // batches up to this size use growth ratio 8
     int shadow_param = 0;          // 16-bit format of the tensor-core operands: 0 automatic (desired_shadow), 1 bf16, 2 fp16
@@ -398,6 +425,7 @@ int tensor_prepare(knn_index* ix) {
     gemm_plan_set_stages(ix->plan, ix->gemm_stages);
     gemm_plan_set_stream_kernel(ix->plan, ix->stream_kernel);
     gemm_plan_set_small_m128(ix->plan, ix->small_m128);
+    gemm_plan_set_stream_pair(ix->plan, ix->stream_pair);
     return KNN_OK;
 }
 
@@ -536,20 +564,22 @@ struct HostPipe {
         if (slot_q0[w] < 0) return KNN_OK;
         KNN_CHECK_CUDA(cudaEventSynchronize(ix->hp_out_done[w]));
         if (!out_pinned) {
-            memcpy(D + slot_q0[w] * k, ix->hp_pin_D[w].p, size_t(slot_nb[w]) * k * sizeof(float));
-            memcpy(I + slot_q0[w] * k, ix->hp_pin_I[w].p, size_t(slot_nb[w]) * k * sizeof(int64_t));
+            host_copy(D + slot_q0[w] * k, ix->hp_pin_D[w].p, size_t(slot_nb[w]) * k * sizeof(float));
+            host_copy(I + slot_q0[w] * k, ix->hp_pin_I[w].p, size_t(slot_nb[w]) * k * sizeof(int64_t));
         }
         slot_q0[w] = -1;
         return KNN_OK;
     }
-    // before batch b: its queries on the way to the device, `s` ordered behind the copy
+    // before batch b: its queries on the way to the device, `s` ordered behind the copy.  The input slot is free as
+    // soon as the filter of batch b - 2 has read it - NOT when that batch's results are home: its finish phase runs at
+    // low priority under the filter of batch b - 1, and staging the next queries must not wait for it.
     int acquire(int64_t b, int64_t q0, int64_t nb, cudaStream_t s, const float** xq_b, float** D_b, int64_t** I_b) {
         const int w = int(b & 1);
-        KNN_CHECK(drain(w));
+        if (b >= 2) KNN_CHECK_CUDA(cudaEventSynchronize(ix->hp_in_free[w]));
         const size_t bytes = size_t(nb) * ix->d * sizeof(float);
         const float* src = xq + q0 * ix->d;
         if (!in_pinned) {
-            memcpy(ix->hp_pin_xq[w].p, src, bytes);
+            host_copy(ix->hp_pin_xq[w].p, src, bytes);
             src = ix->hp_pin_xq[w].as<float>();
         }
         KNN_CHECK_CUDA(cudaMemcpyAsync(ix->hp_xq[w].p, src, bytes, cudaMemcpyHostToDevice, ix->copy_in));
@@ -560,6 +590,13 @@ struct HostPipe {
         *I_b = ix->hp_I[w].as<int64_t>();
         return KNN_OK;
     }
+    // after the filter of batch b was enqueued on `s`: the input slot can be refilled once it has run
+    int filtered(int64_t b, cudaStream_t s) {
+        KNN_CHECK_CUDA(cudaEventRecord(ix->hp_in_free[int(b & 1)], s));
+        return KNN_OK;
+    }
+    // before the finish phase of batch b is enqueued on `fs`: the output slot's previous rows (batch b - 2) are home
+    int before_finish(int64_t b) { return drain(int(b & 1)); }
     // after the finish phase of batch b was enqueued on `fs`: its rows on the way back
     int release(int64_t b, int64_t q0, int64_t nb, cudaStream_t fs) {
         const int w = int(b & 1);
@@ -632,6 +669,13 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     const int cap = candidate_capacity(k);
     int64_t qb = ix->query_batch;
     if (qb > nq) qb = nq;
+    // A call that fits one batch has nothing to overlap its finish phase with.  Where that phase is heavy (k >= 256:
+    // ~k rows of 4 KB gathered per query) and there are enough queries to keep the GEMM tiles full, the call is cut
+    // into up to four batches so that rescoring runs under the next batch's filter (C2: 14,433 queries, k = 1000).
+    if (ix->overlap_finish && ix->split_single_batch && qb == nq && k >= 256 && nq >= 4096) {
+        const int64_t parts = std::min<int64_t>(4, nq / 2048);
+        qb = (nq + parts - 1) / parts;
+    }
     qb = round_up(qb, 256);
     const int64_t nbatches = (nq + qb - 1) / qb;
     // The finish phase of a batch (exact rescoring + final select: HBM gathers and shared-memory sorts) runs on a
@@ -648,6 +692,16 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
     // a previous call's side-stream work (possibly issued from another stream) still owns the workspaces
     KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[0], 0));
     KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[1], 0));
+    // Overlapped: the filter phase moves to an internal HIGH-priority stream and the finish phase runs on a
+    // LOW-priority one.  Without that the thousands of short rescoring CTAs, enqueued first, are dispatched ahead of
+    // the next GEMM launches and the two phases merely swap places; with it a GEMM CTA takes the first slot that
+    // frees up and rescoring fills what the resident GEMM CTAs leave (registers, ~64 KB of shared memory, HBM).
+    cudaStream_t caller = s;
+    if (overlap) {
+        KNN_CHECK_CUDA(cudaEventRecord(ix->ev_fork, caller));
+        KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->hi, ix->ev_fork, 0));
+        s = ix->hi;
+    }
     for (int64_t b = 0; b < nbatches; ++b) {
         const int64_t q0 = b * qb;
         const int64_t nb = nq - q0 < qb ? nq - q0 : qb;
@@ -658,6 +712,10 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
         if (hp) KNN_CHECK(hp->acquire(b, q0, nb, s, &xq_b, &D_b, &I_b));
         if (overlap && b >= 2) KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[w], 0));  // ws1[w] is free again
         KNN_CHECK(tensor_filter_batch(ix, ix->ws1[w], 0, nb, xq_b, k, cap, ix->overflow.as<int>() + b, ix->ovf_q.as<int>() + q0, s));
+        if (hp) {
+            KNN_CHECK(hp->filtered(b, s));
+            KNN_CHECK(hp->before_finish(b));
+        }
         cudaStream_t fs = s;
         if (overlap) {
             fs = ix->side;
@@ -668,7 +726,10 @@ int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* 
         if (overlap) KNN_CHECK_CUDA(cudaEventRecord(ix->ev_finished[w], fs));
         if (hp) KNN_CHECK(hp->release(b, q0, nb, fs));
     }
-    if (overlap) {  // the caller's stream sees every result
+    if (overlap) {  // the caller's stream sees every result (and the per-batch overflow flags)
+        KNN_CHECK_CUDA(cudaEventRecord(ix->ev_join, s));
+        s = caller;
+        KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_join, 0));
         KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[0], 0));
         KNN_CHECK_CUDA(cudaStreamWaitEvent(s, ix->ev_finished[1], 0));
     }
@@ -818,13 +879,19 @@ int knn_index_create(knn_index** out, int d, int metric, int device, unsigned fl
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->add_event, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->search_event, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->side, cudaStreamNonBlocking);
+    int prio_least = 0, prio_greatest = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ix->side, cudaStreamNonBlocking, prio_least);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ix->hi, cudaStreamNonBlocking, prio_greatest);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->copy_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->copy_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&ix->hp_in_ready[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->hp_out_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->hp_computed[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->hp_in_free[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->stage_free[i], cudaEventDisableTiming);
     }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -847,13 +914,14 @@ int knn_index_free(knn_index* ix) {
     DeviceGuard g(ix->device);
     cudaStreamSynchronize(ix->stream);
     if (ix->side) cudaStreamSynchronize(ix->side);
+    if (ix->hi) cudaStreamSynchronize(ix->hi);
     for (DevBuf* b : {&ix->stage, &ix->xq_f32, &ix->xnorm2, &ix->eps, &ix->scores, &ix->lists_s, &ix->lists_i,
                       &ix->overflow, &ix->ovf_q, &ix->ovf_idx, &ix->ovf_x, &ix->ovf_D, &ix->ovf_I, &ix->h_xq, &ix->h_D, &ix->h_I})
         b->release();
     for (int i = 0; i < 2; ++i) {
         ix->hp_xq[i].release(); ix->hp_D[i].release(); ix->hp_I[i].release();
         ix->hp_pin_xq[i].release(); ix->hp_pin_D[i].release(); ix->hp_pin_I[i].release();
-        for (cudaEvent_t e : {ix->hp_in_ready[i], ix->hp_out_done[i], ix->hp_computed[i], ix->stage_free[i]})
+        for (cudaEvent_t e : {ix->hp_in_ready[i], ix->hp_out_done[i], ix->hp_computed[i], ix->stage_free[i], ix->hp_in_free[i]})
             if (e) cudaEventDestroy(e);
     }
     ix->stage2.release();
@@ -874,6 +942,9 @@ int knn_index_free(knn_index* ix) {
         if (ix->ev_finished[i]) cudaEventDestroy(ix->ev_finished[i]);
     }
     if (ix->side) cudaStreamDestroy(ix->side);
+    if (ix->hi) cudaStreamDestroy(ix->hi);
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
     if (ix->plan) gemm_plan_destroy(ix->plan);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -1262,6 +1333,8 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "stream_kernel") ix->stream_kernel = value != 0;
     else if (n == "overlap_finish") ix->overlap_finish = value != 0;
     else if (n == "small_m128") ix->small_m128 = value != 0;
+    else if (n == "stream_pair") ix->stream_pair = value != 0;
+    else if (n == "split_single_batch") ix->split_single_batch = value != 0;
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
     else if (n == "small_batch_nq" && value >= 0) ix->small_batch_nq = value;
 #ifdef KNN_EXPERIMENTS  // measurement aid that skips the epilogue (wrong results): never part of the shipped ABI

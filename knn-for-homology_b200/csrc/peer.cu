@@ -8,6 +8,8 @@
 // tournament), and stores the merged row into EVERY rank's output buffer.  One kernel replaces
 // all-gather (G x the payload per rank) + a full merge on every rank: each result row crosses NVLink once in and
 // once out, and every rank merges nq / G queries.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace knn {
@@ -71,6 +73,70 @@ merge_peer_kernel(PeerTable t, int nranks, int64_t q0, int k, int largest) {
             D[r] = key ? key_score(key, largest) : (largest ? -FLT_MAX : FLT_MAX);
             I[r] = key ? int64_t(key_id(key)) : int64_t(-1);
         }
+    }
+}
+
+// ---- bound exchange of the two-phase search, fused into two tiny kernels over peer memory ----
+// Per query batch every shard contributes 2 x batch_rows floats (lower bound on its k-th best score, minus the bound
+// on its j-th best); the combined bound is the element-wise MAX over the shards.  An NCCL all-reduce per batch would
+// do, but its kernel wants ~100 registers x 640 threads: it does not fit next to the resident GEMM CTA and would take
+// an SM from the next panel launch.  Instead: `push` stores this rank's slice into slot [rank] of EVERY rank's buffer
+// (NVLink stores), fences, and raises flag [rank] there to the call's epoch; `wait_max` (32 threads per CTA, a few
+// registers: co-resident with anything) spins on the local flags of all ranks and then reduces the local slots.
+// No rank ever waits inside a kernel for something that depends on its own later work, so there is no cycle; a
+// bounded spin (~4 s) turns a lost peer into an error flag instead of a hang.
+struct BoundsPeers {
+    float* slots[kMaxPeers];       // rank l's slot array [nranks][n] (for this batch)
+    unsigned* flags[kMaxPeers];    // rank l's flags [nranks]          (for this batch)
+};
+
+__global__ void __launch_bounds__(256)
+bounds_push_kernel(BoundsPeers t, int nranks, int rank, int64_t n, const float* __restrict__ src, unsigned epoch,
+                   unsigned* __restrict__ done_counter) {
+    const int64_t total = int64_t(nranks) * n;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int dst = int(i / n);
+        const int64_t e = i - int64_t(dst) * n;
+        t.slots[dst][int64_t(rank) * n + e] = src[e];
+    }
+    __threadfence_system();  // this thread's stores are visible system-wide before the counter / flags move
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned arrived = atomicAdd(done_counter, 1u) + 1u;
+        if (arrived == gridDim.x) {  // last CTA: every store of the grid is fenced
+            *done_counter = 0;
+            __threadfence_system();
+            for (int dst = 0; dst < nranks; ++dst)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.flags[dst] + rank), "r"(epoch) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bounds_wait_max_kernel(const float* __restrict__ slots, const unsigned* __restrict__ flags, int nranks, int64_t n, unsigned epoch,
+                       float* __restrict__ out, int* __restrict__ timeout_flag) {
+    if (threadIdx.x < nranks) {
+        const unsigned* f = flags + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (int(v - epoch) >= 0) break;
+            if (clock64() - t0 > 8000000000ll) {  // ~4 s at 2 GHz: a peer never arrived
+                atomicExch(timeout_flag, 1);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        float m = -FLT_MAX;
+        for (int r = 0; r < nranks; ++r) {
+            const float v = __ldcg(slots + int64_t(r) * n + i);  // written by a peer over NVLink: read at L2
+            m = v > m ? v : m;
+        }
+        out[i] = m;
     }
 }
 
@@ -138,6 +204,44 @@ int knn_peer_handle_open(const unsigned char* handle64, int device, void** out) 
 
 int knn_peer_handle_close(void* p) {
     if (p) KNN_CHECK_CUDA(cudaIpcCloseMemHandle(p));
+    return KNN_OK;
+}
+
+int knn_bounds_push_peer_dev(int nranks, int rank, int64_t n, const float* src_dev, void* const* slots_peer,
+                             void* const* flags_peer, uint32_t epoch, uint32_t* counter_dev, void* stream) {
+    if (nranks <= 0 || nranks > kMaxPeers || rank < 0 || rank >= nranks || n <= 0 || !src_dev || !slots_peer || !flags_peer || !counter_dev) {
+        set_error("bounds_push: invalid arguments (at most %d ranks)", kMaxPeers);
+        return KNN_ERR_INVALID;
+    }
+    BoundsPeers t;
+    memset(&t, 0, sizeof(t));
+    for (int l = 0; l < nranks; ++l) {
+        if (!slots_peer[l] || !flags_peer[l]) {
+            set_error("bounds_push: null peer pointer for rank %d", l);
+            return KNN_ERR_INVALID;
+        }
+        t.slots[l] = static_cast<float*>(slots_peer[l]);
+        t.flags[l] = static_cast<unsigned*>(flags_peer[l]);
+    }
+    PtrDeviceGuard g(src_dev);
+    const int64_t total = int64_t(nranks) * n;
+    const int grid = int(std::min<int64_t>(32, (total + 255) / 256));
+    bounds_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, nranks, rank, n, src_dev, epoch, counter_dev);
+    KNN_CHECK_LAUNCH();
+    return KNN_OK;
+}
+
+int knn_bounds_wait_max_dev(int nranks, int64_t n, const float* slots_dev, const uint32_t* flags_dev, uint32_t epoch,
+                            float* out_dev, int* timeout_flag_dev, void* stream) {
+    if (nranks <= 0 || nranks > kMaxPeers || n <= 0 || !slots_dev || !flags_dev || !out_dev || !timeout_flag_dev) {
+        set_error("bounds_wait_max: invalid arguments");
+        return KNN_ERR_INVALID;
+    }
+    PtrDeviceGuard g(out_dev);
+    const int grid = int(std::min<int64_t>(16, (n + 255) / 256));
+    bounds_wait_max_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(slots_dev, flags_dev, nranks, n, epoch, out_dev,
+                                                                                timeout_flag_dev);
+    KNN_CHECK_LAUNCH();
     return KNN_OK;
 }
 

@@ -47,6 +47,8 @@ SIGNATURES = {
     "knn_peer_handle_get": (ctypes.c_int, [c_vp, c_vp]),
     "knn_peer_handle_open": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "knn_peer_handle_close": (ctypes.c_int, [c_vp]),
+    "knn_bounds_push_peer_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp]),
+    "knn_bounds_wait_max_dev": (ctypes.c_int, [ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp]),
     "knn_merge_topk_peer_dev": (ctypes.c_int, [ctypes.c_int, c_i64, c_i64, ctypes.c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "knn_eval_family_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "knn_eval_levels_dev": (ctypes.c_int, [c_i64, c_i64, c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),

@@ -130,6 +130,68 @@ class PeerExchange:
         self._release()
 
 
+class BoundsExchange:
+    """Per-batch MAX-reduction of the two-phase search's bounds over peer memory (knn_bounds_push_peer_dev /
+    knn_bounds_wait_max_dev).  Every rank owns slots [batch][rank][2 * rows] floats and flags [batch][rank]; a search is
+    one epoch.  Two searches are separated by the barriers of the result merge, so slots are never overwritten while a
+    slower rank still reads them.  All methods are collective in the sense that every rank calls them in the same order."""
+
+    MAX_QUERY_ROWS = 131072 + 16384  # two-phase limit + one padded batch
+
+    def __init__(self, dist, group, rank: int, world: int, device: int):
+        import torch
+
+        from . import _lib
+
+        self._lib, self._check = _lib.load(), _lib.check
+        self.rank, self.world, self.device = rank, world, device
+        self.max_batches = 1024
+        self.flags_off = 0
+        self.slots_off = self.max_batches * world * 4
+        nbytes = self.slots_off + self.MAX_QUERY_ROWS * 2 * world * 4
+        self.ex = PeerExchange(dist, group, rank, world, device)
+        self.ex.ensure(nbytes)
+        self.ex._own_tensor.zero_()
+        self.ex.barrier()  # nobody pushes into a buffer that is not zeroed yet
+        dev = torch.device("cuda", device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.timeout = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch = 0
+        self.n = 0
+
+    def begin(self, nbatches: int, rows: int) -> None:
+        if nbatches > self.max_batches or nbatches * rows > self.MAX_QUERY_ROWS:
+            raise ValueError("too many query batches for the peer bound exchange")
+        self.epoch += 1
+        self.n = 2 * rows
+
+    def max_over_ranks(self, b: int, bounds_b) -> None:
+        """bounds_b (2 * rows floats, contiguous) <- element-wise MAX over the ranks, on the current stream."""
+        import ctypes
+
+        from .index import _torch_stream
+
+        n, w = self.n, self.world
+        slot_b = self.slots_off + b * w * n * 4
+        flag_b = self.flags_off + b * w * 4
+        slots = (ctypes.c_void_p * w)(*[base + slot_b for base in self.ex.bases])
+        flags = (ctypes.c_void_p * w)(*[base + flag_b for base in self.ex.bases])
+        stream = _torch_stream(self.device)
+        self._check(self._lib.knn_bounds_push_peer_dev(w, self.rank, n, bounds_b.data_ptr(), slots, flags, self.epoch,
+                                                       self.counter.data_ptr(), stream))
+        own = self.ex.bases[self.rank]
+        self._check(self._lib.knn_bounds_wait_max_dev(w, n, own + slot_b, own + flag_b, self.epoch, bounds_b.data_ptr(),
+                                                      self.timeout.data_ptr(), stream))
+
+    def check(self) -> None:
+        if int(self.timeout.item()):
+            self.timeout.zero_()
+            raise RuntimeError("bound exchange: a peer rank did not deliver its bounds within the spin limit")
+
+    def close(self) -> None:
+        self.ex.close()
+
+
 def shard_bounds(n: int, world: int, weights=None):
     """Contiguous row ranges: rank r owns [b[r], b[r+1]).  Near-equal by default; with ``weights`` (one positive
     number per rank, e.g. measured_rank_speeds) rank r gets a share of the rows proportional to weights[r]."""
@@ -226,6 +288,10 @@ class ShardedIndexFlat:
         self.peer_merge = peer_merge  # exchange + merge in one kernel over NVLink peer memory (CUDA results only)
         self._exchange = None
         self._side_stream = None
+        self._main_stream = None
+        self._bounds = None
+        # bound exchange of the pipelined two-phase search over NVLink peer memory instead of NCCL (CUDA + NCCL groups)
+        self.peer_bounds = peer_merge and self.world <= 16 and dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.pipeline_batches = True  # exchange + finish of query batch b on a side stream under the filter of batch b + 1
         self.profile_phases = False
         self.last_phases_ms = None
@@ -275,6 +341,9 @@ class ShardedIndexFlat:
         if self._exchange is not None:
             self._exchange.close()
             self._exchange = None
+        if self._bounds is not None:
+            self._bounds.close()
+            self._bounds = None
 
     def adopt_local(self, global_start: int, n_global: int) -> None:
         """Book-keeping for rows that were added straight into ``self.local`` (e.g. generated
@@ -359,10 +428,10 @@ class ShardedIndexFlat:
         as_numpy = isinstance(x, np.ndarray)
         marks = []
 
-        def mark(name):
+        def mark(name, stream=None):
             if self.profile_phases:
                 e = torch.cuda.Event(enable_timing=True)
-                e.record()
+                e.record(stream) if stream is not None else e.record()
                 marks.append((name, e))
 
         mark("start")
@@ -430,33 +499,53 @@ class ShardedIndexFlat:
         import torch
 
         dev = torch.device("cuda", self.local.device)
-        main = torch.cuda.current_stream(dev)
+        caller = torch.cuda.current_stream(dev)
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=dev)
-        side = self._side_stream
+            # priorities: a GEMM CTA of the filter takes the first SM slot that frees up, the thousands of short
+            # rescoring CTAs of the finish phase fill what the resident GEMM CTAs leave (see csrc/index.cu search_tensor)
+            self._side_stream = torch.cuda.Stream(device=dev, priority=0)
+            self._main_stream = torch.cuda.Stream(device=dev, priority=-1)
+        side, main = self._side_stream, self._main_stream
         nq = xd.shape[0]
-        nbatches, rows = self.local.search_begin(xd, k)
-        bounds = torch.zeros((nbatches, 2, rows), dtype=torch.float32, device=dev)
-        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        id_base = self._segments[0][0] if len(self._segments) == 1 else 0
-        j = -(-k // self.world)
-        side.wait_stream(main)  # bounds / D / I exist (allocator streams) before the side stream touches them
-        for b in range(nbatches):
-            self.local.search_filter_batch(b, j, bounds)
-            filtered = torch.cuda.Event()
-            filtered.record(main)
-            with torch.cuda.stream(side):
-                side.wait_event(filtered)
-                self._dist.all_reduce(bounds[b], op=self._dist.ReduceOp.MAX, group=self.group)
-                self.local.search_finish_batch(b, bounds, D, I, id_base)
-        mark("filter")
-        main.wait_stream(side)
-        for t in (bounds, D, I):
+        main.wait_stream(caller)
+        with torch.cuda.stream(main):
+            nbatches, rows = self.local.search_begin(xd, k)
+            bx = self._bounds_exchange(nbatches, rows) if self.peer_bounds else None
+            bounds = torch.zeros((nbatches, 2, rows), dtype=torch.float32, device=dev)
+            D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            id_base = self._segments[0][0] if len(self._segments) == 1 else 0
+            j = -(-k // self.world)
+            side.wait_stream(main)  # bounds / D / I exist before the side stream touches them
+            for b in range(nbatches):
+                self.local.search_filter_batch(b, j, bounds)
+                filtered = torch.cuda.Event()
+                filtered.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(filtered)
+                    if bx is not None:   # two tiny kernels over NVLink peer memory (csrc/peer.cu): fit next to the GEMM
+                        bx.max_over_ranks(b, bounds[b])
+                    else:                # NCCL: its kernel waits for a panel boundary of the GEMM on the main stream
+                        self._dist.all_reduce(bounds[b], op=self._dist.ReduceOp.MAX, group=self.group)
+                    self.local.search_finish_batch(b, bounds, D, I, id_base)
+            mark("filter", main)
+            main.wait_stream(side)
+            mark("exchange_finish_exposed", main)
+            self.local.search_end(D, I, id_base)
+        caller.wait_stream(main)
+        for t in (bounds, D, I, xd):
             t.record_stream(side)
-        mark("exchange_finish_exposed")
-        self.local.search_end(D, I, id_base)
+            t.record_stream(main)
+            t.record_stream(caller)
+        if bx is not None:
+            bx.check()
         return D, I
+
+    def _bounds_exchange(self, nbatches: int, rows: int):
+        if self._bounds is None:
+            self._bounds = BoundsExchange(self._dist, self.group, self.rank, self.world, self.local.device)
+        self._bounds.begin(nbatches, rows)
+        return self._bounds
 
     def _merge_over_peer_memory(self, D, I):
         """This rank merges its slice of the queries out of the peers' memory and stores the merged rows into every

@@ -116,7 +116,9 @@ def _write_back(host: np.ndarray, dev) -> None:
     """faiss.normalize_L2 mutates the caller's float32 C-contiguous array; anything else it refuses."""
     if host.dtype != np.float32 or not host.flags.c_contiguous:
         raise TypeError("normalize_L2 expects a C-contiguous float32 array (it normalises in place)")
-    host[...] = dev.cpu().numpy()
+    import torch
+
+    torch.from_numpy(host).copy_(dev)  # device -> the caller's memory directly (no intermediate host copy)
 
 
 def proteins_search(full_sequences_data: Path, index_mode: str = "flat", k: int = 1000, device: int | None = None):

@@ -19,9 +19,13 @@ is SURVEY.md section 8(c)'s, all of it:
   without the extra columns a foreign id at the boundary is arbitrated against the id it
   displaced;
 * no id may appear twice in a row, padding (-1) must match exactly;
-* ``|D - D_ref| <= 1e-5*|D_ref|`` - strictly the stated relative bound - wherever
-  ``|D_ref| > 100*tau``; only for scores that close to zero, where a relative bound says
-  nothing about an fp32 sum of d products, the absolute bound ``tau`` applies instead.
+* ``|D - D_ref| <= max(1e-5*|D_ref|, tau/8)``: strictly the stated relative bound - no
+  additive slack - wherever it is physically meaningful.  ``tau/8`` (= 8 ulp of a
+  scale-sized float at d = 1024) is the noise floor of an fp32 sum of d products: two valid
+  fp32 evaluations of the same score (another summation order; for L2 the reference's own
+  ``|x|^2+|y|^2-2<x,y>``, which cancels) differ by that much however small the score is,
+  so below ``|D_ref| = 12500*tau`` (0.048 for unit vectors at d = 1024; C4's scores are
+  0.13 and up) the relative bound cannot be what BASELINE.json means and the floor applies.
 
 Returned: the number of excused positions (tests bound it) and ``max_rel_err_D``, the
 largest relative distance error over the positions the relative bound applies to.
@@ -92,14 +96,15 @@ def check_parity(D, I, D_ref, I_ref, xq, xb, metric, *, rtol=1e-5, max_excused_f
     tau_q = (tau_unit * scale)[:, None]  # absolute tie tolerance per query
     ref64 = D_ref.astype(np.float64)
     err = np.abs(D.astype(np.float64) - ref64)
-    relative = (np.abs(ref64) > 100.0 * tau_q) & ~pad  # the stated 1e-5 relative bound applies
+    floor = tau_q / 8.0  # fp32 accumulation noise floor (see the module docstring)
+    relative = (rtol * np.abs(ref64) >= floor) & ~pad  # the stated 1e-5 relative bound applies
     near_zero = ~relative & ~pad
-    bad = (relative & (err > rtol * np.abs(ref64))) | (near_zero & (err > tau_q))
+    bad = (relative & (err > rtol * np.abs(ref64))) | (near_zero & (err > floor))
     if bad.any():
         r, c = np.argwhere(bad)[0]
         raise ParityError(
             "distance mismatch at (%d,%d): %r vs ref %r (%s bound); %d bad of %d"
-            % (r, c, D[r, c], D_ref[r, c], "relative 1e-5" if relative[r, c] else "near-zero tau", int(bad.sum()), bad.size)
+            % (r, c, D[r, c], D_ref[r, c], "relative 1e-5" if relative[r, c] else "near-zero tau/8", int(bad.sum()), bad.size)
         )
     max_rel = float((err[relative] / np.abs(ref64[relative])).max()) if relative.any() else 0.0
 

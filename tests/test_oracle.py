@@ -172,14 +172,14 @@ def test_parity_checker_excuses_only_fp32_near_ties():
 
 def test_parity_checker_distance_bound_is_the_stated_1e5_relative():
     """BASELINE.json: 'distances must agree within 1e-5 relative' - no additive slack for scores away from zero;
-    only scores within 100 tau of zero fall back to the absolute tie tolerance."""
+    only below the fp32 noise floor (tau / 8 absolute) does the absolute bound take over."""
     rng = np.random.default_rng(5)
     xb = rng.standard_normal((400, 1024)).astype(np.float32)
     xq = rng.standard_normal((3, 1024)).astype(np.float32)
     xb /= np.linalg.norm(xb, axis=1, keepdims=True)
     xq /= np.linalg.norm(xq, axis=1, keepdims=True)
     D, I = fo.knn_flat(xq, xb, 6, 0)
-    assert D.min() > 100 * 2 * 32 * 2.0 ** -24  # every score is in the relative regime
+    assert 1e-5 * D.min() > 2 * 32 * 2.0 ** -24 / 8  # every score is in the relative regime
     ok = D * np.float32(1 + 5e-6)
     assert check_parity(ok, I, D, I, xq, xb, 0)["max_rel_err_D"] == pytest.approx(5e-6, rel=0.2)
     # 4e-5 relative passed the old checker at this magnitude (its additive tau term); the stated bar rejects it

@@ -31,10 +31,11 @@ int main() {
     for (int cluster = 1; cluster <= 2; ++cluster) {
         for (int big_smem : {165136, 100000, 220000}) {
             for (int small_smem : {0, 4096, 34320})
-            for (int carve : {-1, 100}) {  // preferred shared-memory carveout of the small kernel: driver default / max shared
+            for (int carve : {-1, 100}) {  // preferred shared-memory carveout of BOTH kernels: driver default / max shared
                 cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, 230000);
                 cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
                 cudaFuncSetAttribute(small_k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+                cudaFuncSetAttribute(big, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(148); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = big_smem; cfg.stream = a;
                 cudaLaunchAttribute at[1];
