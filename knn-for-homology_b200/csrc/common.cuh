@@ -149,7 +149,8 @@ int launch_scan_f32(const float* xq_f32, const float* xnorm2, int64_t nq, int dp
 // kernel); other slots get id = kInvalidId.
 int launch_rerank(const float* xq_f32, const float* xnorm2, int64_t nq, int dp, const float* xb_f32,
                   const __nv_bfloat16* xb_bf16, const float* ynorm2, int metric, float* cand_scores,
-                  uint32_t* cand_ids, const int* counts, const float* tau, int cap, cudaStream_t s);
+                  uint32_t* cand_ids, const int* counts, const float* tau, int cap, int64_t ntotal, int k, int l2_blocked,
+                  cudaStream_t s);
 
 // select.cu
 // Level 1: dense rows -> per (query, segment) best-k appended to lists[q][seg*k + r].

@@ -182,6 +182,7 @@ struct knn_index {
     int gemm_stages = 0;
     int stream_kernel = 1;
     int stream_pair = 1;
+    int l2_blocked_rerank = 1;
     int small_m128 = 0;  // measured slower than the CTA-pair tiles (5.9 vs 4.6 ms at 128 queries x 10M rows): off
     int panel_ratio = 0;  // 0: automatic
     int64_t small_batch_nq = 256;  // batches up to this size use growth ratio 8
@@ -488,7 +489,8 @@ int tensor_finish_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     if (lower) KNN_CHECK(launch_apply_lower(st.thr, W.eps.as<float>() + off, lower, neg_lower2, nb, s));
     if (ix->profile) cudaEventRecord(next_event_r(ix), s);
     KNN_CHECK(launch_rerank(W.xq_f32.as<float>() + off * ix->dp, W.xnorm2.as<float>() + off, nb, ix->dp, ix->xb_f32,
-                            bf16_rows(ix), ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, s));
+                            bf16_rows(ix), ix->ynorm2, ix->metric, st.cand_scores, st.cand_ids, st.counts, st.thr, cap, ix->ntotal, k,
+                            ix->l2_blocked_rerank, s));
     if (ix->profile) cudaEventRecord(next_event_r(ix), s);
     KNN_CHECK(launch_select_final(st.cand_scores, st.cand_ids, st.counts, cap, 0, nb, k, largest, D, I, id_base, s));
     return KNN_OK;
@@ -1334,6 +1336,7 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "overlap_finish") ix->overlap_finish = value != 0;
     else if (n == "small_m128") ix->small_m128 = value != 0;
     else if (n == "stream_pair") ix->stream_pair = value != 0;
+    else if (n == "l2_blocked_rerank") ix->l2_blocked_rerank = value != 0;
     else if (n == "split_single_batch") ix->split_single_batch = value != 0;
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);
     else if (n == "small_batch_nq" && value >= 0) ix->small_batch_nq = value;

@@ -8,6 +8,8 @@
 //   normalize_l2_kernel  <- faiss.normalize_L2        (cath/search.py:19, seqvec_search/main.py:31,34)
 //   ingest_rows_kernel   <- IndexFlat.add             (cath/search.py:22, pfam/proteins_search.py:37)
 //   scan_f32_kernel      <- IndexFlat.search, fp32    (cath/search.py:24, seqvec_search/main.py:45)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace knn {
@@ -275,15 +277,24 @@ __device__ __forceinline__ float4 chunk_to_f32(const uint2& p) {
 // coalesced load, then walks the entries that passed the final threshold NR at a time (2 fp32 rows or 4 bf16
 // rows: 8 KB in flight per warp either way): all loads of the NR rows are issued before the FMAs consume them.
 // The FMA order per (row, query) pair is the scan kernel's, so a pair gets the same bits whichever path scored it.
+//
+// L2-blocked form (range_rows < number of rows): the grid is (row range, query) with the RANGE as the slow index, and
+// a CTA rescoring only the candidates whose row lies in its range.  CTAs are dispatched in grid order, so at any time
+// the resident CTAs of all SMs gather from one or two adjacent ranges of ~48 MB: a row crosses HBM once per query
+// batch and is served from L2 to every other query that lists it.  With k = 1000 against 300k rows (C3) a batch lists
+// every row ~59 times: 72 GB of row gathers per batch, of which 1.2 GB come from HBM.
 template <bool BF16DB, int NR, int U, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, int dp, const void* __restrict__ xb,
               const float* __restrict__ ynorm2, int metric, float* __restrict__ cand_scores,
               uint32_t* __restrict__ cand_ids, const int* __restrict__ counts, const float* __restrict__ tau,
-              int cap) {
+              int cap, unsigned nq, unsigned range_rows) {
     using Raw = typename RowChunk<BF16DB>::T;  // NR rows x U chunks per lane in flight
     extern __shared__ float4 sq[];  // [dp/4]
-    const int64_t q = blockIdx.x;
+    const int64_t q = blockIdx.x % nq;
+    const unsigned range = blockIdx.x / nq;
+    const uint32_t id_lo = range * range_rows;                       // candidates of this CTA: id_lo <= id <= id_hi
+    const uint32_t id_hi = range_rows >= kInvalidId - id_lo ? kInvalidId - 1u : id_lo + range_rows - 1u;
     const int dp4 = dp / 4;
     for (int i = threadIdx.x; i < dp4; i += blockDim.x)
         sq[i] = reinterpret_cast<const float4*>(xq + q * int64_t(dp))[i];
@@ -304,11 +315,13 @@ rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, in
         const int i = base + lane;
         float approx = 0.f;
         uint32_t id = kInvalidId;
+        bool here = false;  // this CTA decides the entry (it is touched by exactly one CTA: never rescored twice)
         if (i < cnt && mine) {
-            approx = cs[i];
             id = ci[i];
+            here = id >= id_lo && id <= id_hi;
+            if (here) approx = cs[i];
         }
-        const bool valid = (i < cnt) && mine && (approx >= t) && id != kInvalidId;
+        const bool valid = here && (approx >= t);
         unsigned mask = __ballot_sync(0xffffffffu, valid);
         float res = 0.f;
         while (mask) {  // warp-uniform
@@ -363,7 +376,7 @@ rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, in
                 }
             }
         }
-        if (i < cnt && mine) {
+        if (here) {
             if (valid) cs[i] = res;
             else ci[i] = kInvalidId;
         }
@@ -480,18 +493,33 @@ int launch_scan_f32(const float* xq_f32, const float* xnorm2, int64_t nq, int dp
 
 int launch_rerank(const float* xq_f32, const float* xnorm2, int64_t nq, int dp, const float* xb_f32,
                   const __nv_bfloat16* xb_bf16, const float* ynorm2, int metric, float* cand_scores,
-                  uint32_t* cand_ids, const int* counts, const float* tau, int cap, cudaStream_t s) {
+                  uint32_t* cand_ids, const int* counts, const float* tau, int cap, int64_t ntotal, int k, int l2_blocked,
+                  cudaStream_t s) {
     if (nq <= 0) return KNN_OK;
     const size_t smem = size_t(dp) * sizeof(float);
     // fewer queries than a couple of CTAs per SM: every list is shared by `split` CTAs (a power of two <= 8)
     int split = 1;
     while (split < 8 && nq * split < 2 * int64_t(num_sms())) split *= 2;
-    const dim3 grid = dim3(unsigned(nq), unsigned(split), 1);
+    // L2-blocked (see the kernel): when the batch lists every row several times (nq k > 4 N) and the rows do not fit
+    // L2 anyway, walk the database in ranges of ~48 MB of rows
+    const int64_t row_bytes = int64_t(dp) * (xb_f32 ? 4 : 2);
+    int64_t range_rows = int64_t(1) << 32;
+    int64_t n_ranges = 1;
+    if (l2_blocked && split == 1 && nq * int64_t(k) > 4 * ntotal && ntotal * row_bytes > (int64_t(64) << 20)) {
+        range_rows = std::max<int64_t>(1024, (int64_t(48) << 20) / row_bytes);
+        n_ranges = (ntotal + range_rows - 1) / range_rows;
+        if (n_ranges * nq > 0x7FFFFFFFll) {
+            range_rows = int64_t(1) << 32;
+            n_ranges = 1;
+        }
+    }
+    const dim3 grid = dim3(unsigned(nq * n_ranges), unsigned(split), 1);
+    const unsigned rr = range_rows >= (int64_t(1) << 32) ? 0xFFFFFFFFu : unsigned(range_rows);
 #define KNN_RERANK(BF, NRV, UV, MINBV, XB)                                                                             \
     {                                                                                                                  \
         auto kern = rerank_kernel<BF, NRV, UV, MINBV>;                                                                 \
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));            \
-        kern<<<grid, kBlock, smem, s>>>(xq_f32, xnorm2, dp, XB, ynorm2, metric, cand_scores, cand_ids, counts, tau, cap); \
+        kern<<<grid, kBlock, smem, s>>>(xq_f32, xnorm2, dp, XB, ynorm2, metric, cand_scores, cand_ids, counts, tau, cap, unsigned(nq), rr); \
     }
     // 8 KB in flight per warp either way.  Measured on B200 (4M x 1024 fp32 rows, 16384 queries, k = 1000): 2 x 8, 4 x 4,
     // 4 x 8 and 2 x 4 (rows x chunks) with 1-4 CTAs per SM all take 23.1-24.2 ms - the gather of 4 KB rows is not

@@ -639,3 +639,35 @@ def test_two_phase_sharded_search_equals_single_index(knn, metric, normalize):
     assert (lo == -np.finfo(np.float32).max).all()
     d_, i_ = small.search_finish(lower, k)
     assert i_.shape == (300, k)
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_l2_blocked_rerank_and_overlapped_batches_change_nothing(knn, metric):
+    """Rescoring-heavy shape (nq k > 4 N, rows larger than 64 MB): the rerank walks the database in L2-sized row
+    ranges (grid = range x query), a call of several query batches runs the finish phase of batch b on a side stream
+    under the filter of batch b + 1, and a single-batch call with k >= 256 is cut into batches for the same reason.
+    None of it may change a bit of the result: compared with the exact scan and with every switch off."""
+    xq, xb = _data(4500, 20000, 1024, seed=77, normalize=metric == IP, scale=1.0)
+    xb[15000:15040] = xb[100]  # duplicates straddling the two row ranges (12,288 rows of 4 KB each)
+    k = 300
+    D1, I1, _ = _search(knn, xq[:600], xb, k, metric, path=1)
+    base = None
+    for switches in ({}, {"l2_blocked_rerank": 0}, {"overlap_finish": 0}, {"split_single_batch": 0},
+                     {"query_batch": 1024}, {"query_batch": 1024, "overlap_finish": 0, "l2_blocked_rerank": 0}):
+        D, I, idx = _search(knn, xq, xb, k, metric, path=2, **switches)
+        assert idx.stat("path") == 2 and idx.stat("overflow_batches") == 0, switches
+        if base is None:
+            base = (D, I)
+            assert np.array_equal(I[:600], I1) and np.array_equal(D[:600], D1)
+        assert np.array_equal(I, base[1]) and np.array_equal(D, base[0]), switches
+    D_ref, I_ref = fo.knn_flat(xq[:200], xb, k, metric, want=k + 4)
+    check_parity(base[0][:200], base[1][:200], D_ref, I_ref, xq[:200], xb, metric, max_excused_frac=1e-2)
+    # host path (numpy in / out, pipelined per batch) returns the same bits as the device path
+    import torch
+
+    idx = knn.IndexFlat(1024, metric)
+    idx.set_param("path", 2)
+    idx.set_param("query_batch", 1024)
+    idx.add(xb)
+    Dd, Id = idx.search(torch.from_numpy(xq).cuda(), k)
+    assert np.array_equal(Id.cpu().numpy(), base[1]) and np.array_equal(Dd.cpu().numpy(), base[0])
