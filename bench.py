@@ -383,11 +383,7 @@ def main():
         if world == 1:
             last["np"] = index.local.search(xq_np, args.k)  # IndexFlat.search(numpy) -> numpy: what `index.search` is to the drivers
         else:
-            xq = index.upload_queries(xq_np) if Q == 1 else torch.from_numpy(xq_np).to(dev)
-            D, I = index.search(xq, args.k)
-            if rank == 0:
-                last["np"] = (D.cpu().numpy(), I.cpu().numpy())
-            torch.cuda.synchronize()
+            last["np"] = index.search(xq_np, args.k)  # numpy in, numpy out on every rank (sharded upload inside)
 
     by_rank = {}
 
@@ -439,7 +435,7 @@ def main():
         ms_e, _, _, _ = timed(step_e2e, args.steps, 1)
         e2e = {"value": args.nq * args.steps / (ms_e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps, "host_memory": "pinned"}
-        ms_p, _, _, _ = timed(step_e2e_pageable, args.steps, 1)
+        ms_p, _, _, _ = timed(step_e2e_pageable, args.steps, 2)  # 2 warm-ups: both result buffers of the pinned-memory cache exist
         e2e_pageable = {"value": args.nq * args.steps / (ms_p / 1e3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_p / args.steps,
                         "host_memory": "pageable numpy arrays in and out (the reference drivers' call)"}
@@ -492,7 +488,14 @@ def main():
             gbs = nbytes / (ms_call / 1e3) / 1e9
             launches_per_call = (lib.knn_kernel_launches() - l0) // reps
             Ds, Is = search(xs, args.k)
+            tfl = 2.0 * nq_s * args.nb * D_DIM / (ms_call / 1e3) / 1e12
             small.append({"nq": nq_s, "ms_per_call": ms_call, "gbs": gbs, "frac_of_hbm": gbs / peaks_hbm,
+                          # 129..256 queries sit at the machine balance (2*256*d flop per 2*d bytes of a bf16 row): the
+                          # call keeps the tensor pipe AND HBM busy and runs into the board power cap (ncu: SM clock
+                          # 1.16 GHz, tensor pipe 98 % active, profiles/r01_gemm_main_ncu_nq256.md)
+                          "tflops": tfl, "frac_of_tensor_sustained": tfl / measured_peaks()["tflops_sustained"],
+                          "kernel": ("gemm_stream_kernel (queries resident in shared memory)" if nq_s <= 64 else
+                                     "gemm_stream_kernel, CTA pair" if nq_s <= 128 else "gemm_filter_kernel, one 256-query tile pair"),
                           "launches_per_call": launches_per_call,
                           "identical_to_large_batch_result": bool(torch.equal(Is, I[:nq_s]) and torch.equal(Ds, D[:nq_s]))})
 

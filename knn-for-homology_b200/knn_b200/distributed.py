@@ -192,6 +192,24 @@ class BoundsExchange:
         self.ex.close()
 
 
+def _to_numpy(t):
+    """Result tensor -> numpy.  CUDA results travel straight into page-locked memory (ordinary numpy arrays to the
+    caller, see index._result_arrays) instead of through the driver's pageable bounce buffers."""
+    if not t.is_cuda:
+        return t.numpy()
+    import torch
+
+    if 0 < t.numel() * t.element_size() <= (1 << 30):
+        try:
+            out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            out.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            return out.numpy()
+        except RuntimeError:
+            pass
+    return t.cpu().numpy()
+
+
 def shard_bounds(n: int, world: int, weights=None):
     """Contiguous row ranges: rank r owns [b[r], b[r+1]).  Near-equal by default; with ``weights`` (one positive
     number per rank, e.g. measured_rank_speeds) rank r gets a share of the rows proportional to weights[r]."""
@@ -426,6 +444,10 @@ class ShardedIndexFlat:
         import torch
 
         as_numpy = isinstance(x, np.ndarray)
+        on_cuda = self._dist.is_initialized() and self._dist.get_backend(self.group) == "nccl"
+        if as_numpy and on_cuda and self.world > 1:
+            # host queries that every rank holds: each rank uploads 1/G of them, one all-gather over NVLink does the rest
+            x = self.upload_queries(x)
         marks = []
 
         def mark(name, stream=None):
@@ -439,13 +461,13 @@ class ShardedIndexFlat:
                      and x.shape[0] <= self.TWO_PHASE_MAX_QUERIES)
         globalised = False
         if two_phase and self.pipeline_batches and hasattr(self.local, "search_begin"):
-            xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if as_numpy else x
+            xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if isinstance(x, np.ndarray) else x
             D, I = self._two_phase_pipelined(xd, k, mark)
             globalised = len(self._segments) == 1
         elif two_phase:
             # filter on every shard -> all-reduce(MAX) of the per-query lower bounds of the k-th best score ->
             # each shard rescoring only what can still be in the global top-k
-            xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if as_numpy else x
+            xd = torch.from_numpy(x).to(torch.device("cuda", self.local.device)) if isinstance(x, np.ndarray) else x
             # two bounds on the global k-th best true score: the best shard's own k-th, and - every shard holding
             # j = ceil(k/G) rows at or above its own j-th - the smallest j-th over the shards
             j = -(-k // self.world)
@@ -460,10 +482,9 @@ class ShardedIndexFlat:
             mark("finish")
         else:
             D, I = self.local.search(x, k)
-            if as_numpy:
+            if isinstance(D, np.ndarray):
                 D, I = torch.from_numpy(D), torch.from_numpy(I)
-                backend = self._dist.get_backend(self.group) if self._dist.is_initialized() else "gloo"
-                if backend == "nccl":
+                if on_cuda:
                     dev = torch.device("cuda", self.local.device)
                     D, I = D.to(dev), I.to(dev)
         if not globalised:
@@ -485,7 +506,7 @@ class ShardedIndexFlat:
             torch.cuda.synchronize()
             self.last_phases_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
         if as_numpy:
-            return D.cpu().numpy(), I.cpu().numpy()
+            return _to_numpy(D), _to_numpy(I)
         return D, I
 
     def _two_phase_pipelined(self, xd, k: int, mark):
@@ -665,7 +686,7 @@ class GridIndexFlat:
         D = torch.cat([bufD[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
         I = torch.cat([bufI[g * chunk:g * chunk + (b[g + 1] - b[g])] for g in range(self.Q)])
         if as_numpy:
-            return D.cpu().numpy(), I.cpu().numpy()
+            return _to_numpy(D), _to_numpy(I)
         return D, I
 
     def close(self) -> None:

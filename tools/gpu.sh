@@ -12,6 +12,9 @@
 #   launches[:args]  ncu launch list (gpu__time_duration) of bench.py <args>
 #   ncu:<kernel-regex>[:args]  one ncu --set full capture of the first launches matching the regex
 #   py:<script>[:args]  python <script> <args>
+#   prof:<name>:<kernel-regex>:<script+args>   ncu --set full --profile-from-start off of the launches matching the regex
+#                        in a script that brackets ONE search with cudaProfilerStart/Stop (tools/prof_k.py, prof_small.py)
+#   proflist:<name>:<script+args>              the launch list (gpu__time_duration) of the same bracketed region
 tag=$1; shift
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
@@ -46,6 +49,14 @@ for step in "$@"; do
       kre=${rest%%:*}; nargs=""; [[ "$rest" == *:* ]] && nargs=${rest#*:}; nargs=${nargs//+/ }
       timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$kre" -s 6 -c 3 -o gpurun_out/${tag}_ncu_$(echo "$kre" | tr -c 'a-zA-Z0-9\n' '_') -f \
         python bench.py $nargs > gpurun_out/${tag}_ncu.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/${tag}_ncu.log | cut -c1-200 ;;
+    prof)
+      pname=${rest%%:*}; r2=${rest#*:}; kre=${r2%%:*}; pargs=${r2#*:}; pargs=${pargs//+/ }
+      timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$kre" -c 12 \
+        -o gpurun_out/${tag}_ncu_${pname} -f python $pargs > gpurun_out/${tag}_ncu_${pname}.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/${tag}_ncu_${pname}.log | cut -c1-200 ;;
+    proflist)
+      pname=${rest%%:*}; pargs=${rest#*:}; pargs=${pargs//+/ }
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+        --log-file gpurun_out/${tag}_launches_${pname}.csv python $pargs > gpurun_out/${tag}_launches_${pname}.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/${tag}_launches_${pname}.log | cut -c1-200 ;;
     py)
       script=${rest%%:*}; pargs=""; [[ "$rest" == *:* ]] && pargs=${rest#*:}; pargs=${pargs//+/ }
       f=gpurun_out/${tag}_$(basename $script .py).txt
