@@ -63,8 +63,9 @@ def parse():
     ap.add_argument("--no-phases", action="store_true", help="skip the extra untimed pass that times the phases of the sharded search")
     ap.add_argument("--bf16-storage", action="store_true", help="the bf16 values ARE the database (config C5): no fp32 master rows")
     ap.add_argument("--shadow-fmt", type=int, default=0, choices=[0, 1, 2], help="16-bit format of the tensor-core copy of the database: 0 automatic, 1 bf16, 2 fp16")
-    ap.add_argument("--query-groups", type=int, default=1, help="N > 1: rows x query-groups grid of ranks (GridIndexFlat; not the default: "
-                    "measured on 2 GPUs only, the 8-GPU shape 2 x 4 is unmeasured)")
+    ap.add_argument("--query-groups", type=int, default=0, help="N > 1: Q query groups x (N / Q) row shards (GridIndexFlat).  0 (default): "
+                    "automatic - the largest Q whose row share fits 60 %% of the GPU memory (knn_b200.distributed.choose_query_groups); "
+                    "1: plain row sharding over all N GPUs")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: equal row shards instead of shards proportional to each GPU's measured speed")
     ap.add_argument("--mantissa-bits", type=int, default=0, help="mantissa bits kept in bf16 tensor-core operands: 0 automatic, 2..7")
     ap.add_argument("--config", default="c4", choices=["c4", "c2", "c3", "c5"],
@@ -191,8 +192,8 @@ def workload_config(args, world):
     return {"workload": f"{name}: synthetic normalised {args.nb}x{D_DIM} {store} database, {args.nq} queries, k={args.k}, "
                         f"inner product, exact (ids = fp32 IndexFlatIP on the stored values)",
             "database_rows": args.nb, "queries_per_step": args.nq, "k": args.k, "d": D_DIM,
-            "sharding": (f"rows over {world} GPU(s)" if getattr(args, "query_groups", 1) <= 1 or world == 1 else
-                         f"{args.query_groups} query groups x rows over {world // args.query_groups} GPU(s)"), "l2": "inputs larger than L2 (bf16 database shard >> 126 MB)"}
+            "sharding": f"{world} GPU(s) of one box (the engine's layout over them is reported in `layout`)",
+            "l2": "inputs larger than L2 (bf16 database shard >> 126 MB)"}
 
 
 def gen_block(blk, nb, dev):
@@ -293,7 +294,7 @@ def main():
     import torch.distributed as dist
 
     import knn_b200
-    from knn_b200.distributed import GridIndexFlat, ShardedIndexFlat, measured_rank_speeds, shard_bounds
+    from knn_b200.distributed import GridIndexFlat, ShardedIndexFlat, choose_query_groups, measured_rank_speeds, shard_bounds
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -309,6 +310,9 @@ def main():
         weights = measured_rank_speeds(D_DIM, local_rank, seconds=2.0)
     t_build = time.perf_counter()
     Q = args.query_groups if world > 1 else 1
+    if Q == 0:  # automatic layout
+        Q = choose_query_groups(world, args.nb, D_DIM, 2 if args.bf16_storage else 6, device=local_rank)
+    args.query_groups = Q
     if Q > 1:  # R = world / Q row shards per query group; every group holds the whole database
         index = GridIndexFlat(D_DIM, knn_b200.METRIC_INNER_PRODUCT, query_groups=Q, device=local_rank,
                               bf16_storage=args.bf16_storage, shard_weights=weights)
@@ -372,8 +376,7 @@ def main():
             index.local.search_into(xq_host.data_ptr(), args.nq, args.k, D_host.data_ptr(), I_host.data_ptr())
         else:
             # every rank holds the host queries: each uploads 1/N of them, one all-gather over NVLink does the rest
-            xq = index.upload_queries(xq_host) if Q == 1 else xq_host.to(dev, non_blocking=True)
-            D, I = index.search(xq, args.k)
+            D, I = index.search(xq_host, args.k)  # pinned host tensor in: each rank uploads only its share
             if rank == 0:
                 D_host.copy_(D, non_blocking=True)
                 I_host.copy_(I, non_blocking=True)
@@ -536,6 +539,11 @@ def main():
             "cpu_baseline": cpu, "clocks": clocks, "index_build_s": build_s, "parity_spot_check": parity_ok,
             "search_path": search_path, "cta_group": args.cta_group, "phases_ms_rank0": phases, "ms_per_step_by_rank": by_rank_value or None,
             "shard_rows_by_rank": [b[r + 1] - b[r] for r in range(len(b) - 1)], "query_groups": Q,
+            "layout": {"query_groups": Q, "row_shards_per_group": world // Q,
+                       "note": ("one GPU" if world == 1 else
+                                f"{Q} query group(s) x {world // Q} row shard(s): every group holds the whole database row-sharded over its "
+                                "ranks and answers 1/Q of the queries; chosen as the largest group count whose row share fits 60 % of the "
+                                "GPU memory unless --query-groups says otherwise (1 = plain row sharding)")},
             "rank_speed_weights": [round(w, 4) for w in weights] if weights else None,
             "overlap_finish": not args.no_overlap,
         }

@@ -359,6 +359,23 @@ tighten_kernel(float* __restrict__ thr, int* __restrict__ counts, float* __restr
 // loaded into registers with independent loads (one memory round trip), the k-th largest key is found by a
 // bit-by-bit search (32 rounds of compare + warp reduce), and the survivors are written back compacted - no
 // block-wide barriers, no dependent global loads, 8 queries per CTA.
+// Lowest key bit worth resolving when a value resolution of `res` (> 0) is enough.  Orderable keys are spaced one
+// float ulp apart and the ulp grows with the magnitude, so a key distance of 2^bit spans at most 2^bit ulps of the
+// LARGEST magnitude in the band [mn, mx]: every bit below the returned one resolves less than `res` anywhere in it.
+// (Whatever is returned, clearing low bits of the k-th largest key only lowers it: the bound stays valid.)
+__device__ __forceinline__ int key_resolution_bit(uint32_t mn, uint32_t mx, float res) {
+    if (!(res > 0.f) || mn > mx) return 0;
+    const float m = fmaxf(fabsf(from_orderable_f32(mn)), fabsf(from_orderable_f32(mx)));
+    if (!(m > 0.f) || !(m < FLT_MAX)) return 0;
+    int ex;
+    frexpf(m, &ex);                                    // m = f * 2^ex, f in [0.5, 1): ulp(m) = 2^(ex - 24)
+    const float keys_in_res = ldexpf(res, 24 - ex);    // res / ulp(m)
+    if (!(keys_in_res >= 2.f)) return 0;
+    int bit = 0;
+    while (bit < 30 && ldexpf(1.f, bit + 1) <= keys_in_res) ++bit;  // 2^bit <= keys_in_res
+    return bit;
+}
+
 template <int MAXE>
 __device__ __forceinline__ void warp_tighten_reg(float* __restrict__ cs, uint32_t* __restrict__ ci, int cnt, int k,
                                                  float two_eps, float old_thr, int lane, float& thr_out, int& cnt_out) {
@@ -371,9 +388,32 @@ __device__ __forceinline__ void warp_tighten_reg(float* __restrict__ cs, uint32_
         ids[e] = i < cnt ? ci[i] : kInvalidId;
         keys[e] = (i < cnt && sc == sc) ? orderable_f32(sc) : 0u;
     }
-    uint32_t kth = 0;
+    // Bit-by-bit search of the k-th largest key, on the bits that matter only: the bits all keys share are skipped
+    // (scores of one list live in a narrow band), and the search stops at a resolution of eps / 16 - the prefix found
+    // so far with the remaining bits cleared is a LOWER bound of the k-th largest key, which is all the threshold
+    // needs (it costs ~3 % more candidates and a third of the rounds).
+    uint32_t mn = ~0u, mx = 0u;
+    int nvalid = 0;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        if (keys[e]) {  // 0 = padding / NaN
+            mn = keys[e] < mn ? keys[e] : mn;
+            mx = keys[e] > mx ? keys[e] : mx;
+            ++nvalid;
+        }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    int top = -1, low = 0;
+    uint32_t kth = 0;                     // fewer than k real scores: no bound (the original all-bits search ends at 0)
+    if (nvalid >= k) {
+        top = mn < mx ? 31 - __clz(int(mn ^ mx)) : -1;            // highest bit in which two keys differ
+        low = key_resolution_bit(mn, mx, two_eps * 0.03125f);     // bits below it resolve less than eps / 16
+        kth = top < 0 ? mx : (top >= 31 ? 0u : (mx & ~((2u << top) - 1u)));  // the prefix every key shares
+    }
 #pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
+    for (int bit = top; bit >= low; --bit) {
         const uint32_t cand = kth | (1u << bit);
         int c = 0;
 #pragma unroll

@@ -400,7 +400,7 @@ class ShardedIndexFlat:
         dev = torch.device("cuda", self.local.device) if self._dist.is_initialized() and self._dist.get_backend(self.group) == "nccl" \
             else x_host.device
         if self.world == 1:
-            return x_host.to(dev, non_blocking=True)
+            return x_host.to(dev, non_blocking=True).contiguous()
         chunk = -(-n // self.world)  # equal chunks (all_gather_into_tensor); the tail of the last one is padding
         buf = torch.empty((self.world * chunk, d), dtype=torch.float32, device=dev)
         lo, hi = min(n, self.rank * chunk), min(n, (self.rank + 1) * chunk)
@@ -445,7 +445,7 @@ class ShardedIndexFlat:
 
         as_numpy = isinstance(x, np.ndarray)
         on_cuda = self._dist.is_initialized() and self._dist.get_backend(self.group) == "nccl"
-        if as_numpy and on_cuda and self.world > 1:
+        if on_cuda and (as_numpy or not x.is_cuda):
             # host queries that every rank holds: each rank uploads 1/G of them, one all-gather over NVLink does the rest
             x = self.upload_queries(x)
         marks = []
@@ -591,6 +591,39 @@ class ShardedIndexFlat:
         return D_out.clone(), I_out.clone()
 
 
+def choose_query_groups(world: int, n_rows: int, d: int, bytes_per_element: int, device: int | None = None,
+                        memory_fraction: float = 0.6) -> int:
+    """How many query groups Q (Q divides world; R = world / Q row shards per group) for a database of n_rows x d:
+    the LARGEST Q whose per-rank share of the rows, (n_rows / R) * d * bytes_per_element, fits memory_fraction of the
+    GPU's memory (the rest is for query batches, candidate lists and the caller).  bytes_per_element: 6 for the default
+    storage (fp32 master rows + 16-bit tensor-core rows), 2 for bf16 storage.
+
+    Why larger Q is faster (measured on 8 B200, C4; profiles/r02_bench_c4_8gpu_*.json): row sharding replicates the
+    per-QUERY work of a search - query preparation, threshold tightening after every panel, the exact rescoring and
+    the final select - on every rank of a group, and under the board power cap that work costs its energy whether or
+    not it is overlapped with the GEMM: 8 x 1 row shards 519k queries/s, 2 groups x 4 shards 530k, 4 groups x 2 shards
+    541k.  With 180 GB of HBM per GPU a 10M x 1024 database (61 GB) fits every GPU, so C4 runs as pure query sharding;
+    the 100M-row database of C5 (205 GB in bf16) needs at least two row shards."""
+    total = None
+    try:
+        import torch
+
+        total = torch.cuda.get_device_properties(torch.cuda.current_device() if device is None else device).total_memory
+    except Exception:
+        pass
+    if not total:
+        total = 180 << 30
+    budget = memory_fraction * total
+    best = 1
+    for q in range(1, world + 1):
+        if world % q:
+            continue
+        r = world // q
+        if (n_rows / r) * d * bytes_per_element <= budget:
+            best = q
+    return best
+
+
 class GridIndexFlat:
     """Rows x query-groups grid of ranks (world = R x Q, rank = g * R + r).
 
@@ -666,14 +699,16 @@ class GridIndexFlat:
         as_numpy = isinstance(x, np.ndarray)
         n = x.shape[0]
         lo, hi = self.query_slice(n)
-        D, I = self.inner.search(x[lo:hi], k)
+        on_cuda = self._dist.get_backend(self.col_group) == "nccl"
+        xs = x[lo:hi]
+        if on_cuda and (as_numpy or not xs.is_cuda):
+            # host queries: only this group's slice crosses PCIe (its ranks share the upload), results stay on the device
+            xs = self.inner.upload_queries(xs)
+        D, I = self.inner.search(xs, k)
         if self.Q == 1:
-            return D, I
-        if as_numpy:
+            return (_to_numpy(D), _to_numpy(I)) if as_numpy and not isinstance(D, np.ndarray) else (D, I)
+        if isinstance(D, np.ndarray):
             D, I = torch.from_numpy(D), torch.from_numpy(I)
-            if self._dist.get_backend(self.col_group) == "nccl":  # the column all-gather moves device tensors
-                dev = torch.device("cuda", self.inner.local.device)
-                D, I = D.to(dev), I.to(dev)
         b = self.query_bounds(n)
         chunk = max(b[g + 1] - b[g] for g in range(self.Q))  # equal chunks for all_gather_into_tensor; tails are padding
         bufD = torch.empty((self.Q * chunk, k), dtype=D.dtype, device=D.device)
