@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--no-small-batch", action="store_true", help="N = 1: skip the small-batch (HBM roofline) legs")
     ap.add_argument("--no-overlap", action="store_true", help="finish phase of a batch on the main stream (no side stream)")
     ap.add_argument("--parity-queries", type=int, default=256)
+    ap.add_argument("--param", action="append", default=[], metavar="NAME=VALUE",
+                    help="knn_index_set_param on every rank's index (A/B experiments; results never depend on it)")
     args = ap.parse_args()
     if args.config == "c2":
         args.nb, args.nq, args.k, args.all_vs_all = 14_433, 14_433, 1000, True
@@ -328,6 +330,9 @@ def main():
     if args.shadow_fmt and not args.bf16_storage:
         index.local.set_param("shadow_fmt", args.shadow_fmt)
     index.local.set_param("mantissa_bits", args.mantissa_bits)
+    for kv in args.param:
+        name, _, val = kv.partition("=")
+        index.local.set_param(name, int(val))
     if args.no_overlap:
         index.local.set_param("overlap_finish", 0)
         if Q == 1:
@@ -545,7 +550,7 @@ def main():
                                 "ranks and answers 1/Q of the queries; chosen as the largest group count whose row share fits 60 % of the "
                                 "GPU memory unless --query-groups says otherwise (1 = plain row sharding)")},
             "rank_speed_weights": [round(w, 4) for w in weights] if weights else None,
-            "overlap_finish": not args.no_overlap,
+            "overlap_finish": not args.no_overlap, "params": args.param or None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
