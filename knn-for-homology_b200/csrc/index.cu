@@ -182,7 +182,7 @@ struct knn_index {
     int gemm_stages = 0;
     int stream_kernel = 1;
     int stream_pair = 1;
-    int l2_blocked_rerank = 1;
+    int l2_blocked_rerank = 0;  // opt-in: cuts the rerank's DRAM bytes 10 x but is 2 x slower (see kernels_basic.cu)
     int small_m128 = 0;  // measured slower than the CTA-pair tiles (5.9 vs 4.6 ms at 128 queries x 10M rows): off
     int panel_ratio = 0;  // 0: automatic
     int64_t small_batch_nq = 256;  // batches up to this size use growth ratio 8

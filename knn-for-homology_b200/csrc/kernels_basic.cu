@@ -282,7 +282,12 @@ __device__ __forceinline__ float4 chunk_to_f32(const uint2& p) {
 // a CTA rescoring only the candidates whose row lies in its range.  CTAs are dispatched in grid order, so at any time
 // the resident CTAs of all SMs gather from one or two adjacent ranges of ~48 MB: a row crosses HBM once per query
 // batch and is served from L2 to every other query that lists it.  With k = 1000 against 300k rows (C3) a batch lists
-// every row ~59 times: 72 GB of row gathers per batch, of which 1.2 GB come from HBM.
+// every row ~59 times: 72 GB of row gathers per batch.
+// MEASURED (profiles/r02_ncu_rerank_c3.md, r02_launches_c3_*_l2_blocked_rerank.md): it does what it says - DRAM reads
+// 5.8 GB per batch instead of ~55 GB, L2 hit rate 88 % - and is 2 x SLOWER (18.9 vs 9.7 ms per batch): 409,600 CTAs of
+// ~43 rows each run at 11.6 % warp occupancy, and the 80 GB that cross the L2->SM fabric per batch do so either way.
+// HBM was never the limit of this kernel (the plain form already gathers at 7.4 TB/s, above the HBM roof, thanks to
+// its L2 hits).  Off by default ("l2_blocked_rerank"); kept for databases whose rows are cold in HBM.
 template <bool BF16DB, int NR, int U, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 rerank_kernel(const float* __restrict__ xq, const float* __restrict__ xnorm2, int dp, const void* __restrict__ xb,

@@ -29,11 +29,80 @@ APPROXIMATE_INDEX_HINT = ("%s is an approximate index and not part of this engin
                           "B200 it is faster than the Hamming scan it would replace")
 
 
+_CHUNK_BYTES = 64 << 20
+_pinned = {}
+
+
+def _pinned_pair(device: int):
+    """Two page-locked 64 MB bounce buffers per device: pageable numpy memory <-> device in chunks, the (multi-threaded)
+    host copy of chunk i + 1 under the DMA of chunk i.  A plain pageable cudaMemcpy stages through the driver's own
+    buffers on one thread; the drivers move gigabytes both ways (the reference's in-place normalisation is written back
+    to the caller's arrays), which is most of their wall time once the search takes a fraction of a second."""
+    import torch
+
+    if device not in _pinned:
+        _pinned[device] = [torch.empty(_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    return _pinned[device]
+
+
 def _upload(x: np.ndarray, device: int):
     import torch
 
     x = np.ascontiguousarray(x, dtype=np.float32)
-    return torch.from_numpy(x).to(torch.device("cuda", device))
+    dev = torch.device("cuda", device)
+    if x.nbytes < 2 * _CHUNK_BYTES:
+        return torch.from_numpy(x).to(dev)
+    out = torch.empty(x.shape, dtype=torch.float32, device=dev)
+    src, dst = torch.from_numpy(x).view(-1), out.view(-1)
+    n = _CHUNK_BYTES // 4
+    bufs = [b.view(torch.float32) for b in _pinned_pair(device)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    for c, i in enumerate(range(0, src.numel(), n)):
+        w = c & 1
+        m = min(n, src.numel() - i)
+        if c >= 2:
+            done[w].synchronize()
+        bufs[w][:m].copy_(src[i:i + m])
+        dst[i:i + m].copy_(bufs[w][:m], non_blocking=True)
+        done[w].record()
+    return out
+
+
+def _download_into(host: np.ndarray, dev_tensor) -> None:
+    """Device tensor -> the caller's (pageable) numpy memory, chunked through the pinned pair."""
+    import torch
+
+    t = dev_tensor.contiguous().view(-1)
+    if host.nbytes < 2 * _CHUNK_BYTES or not host.flags.c_contiguous:
+        torch.from_numpy(host).copy_(dev_tensor)
+        return
+    dst = torch.from_numpy(host).view(-1)
+    n = _CHUNK_BYTES // t.element_size()
+    bufs = [b.view(t.dtype) for b in _pinned_pair(dev_tensor.device.index)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    chunks = list(range(0, t.numel(), n))
+    for c, i in enumerate(chunks):  # D2H of chunk c is in flight while chunk c - 1 is copied out on the host
+        w = c & 1
+        m = min(n, t.numel() - i)
+        bufs[w][:m].copy_(t[i:i + m], non_blocking=True)
+        done[w].record()
+        if c >= 1:
+            j = chunks[c - 1]
+            mj = min(n, t.numel() - j)
+            done[w ^ 1].synchronize()
+            dst[j:j + mj].copy_(bufs[w ^ 1][:mj])
+    j = chunks[-1]
+    mj = min(n, t.numel() - j)
+    done[(len(chunks) - 1) & 1].synchronize()
+    dst[j:j + mj].copy_(bufs[(len(chunks) - 1) & 1][:mj])
+
+
+def _to_host(dev_tensor) -> np.ndarray:
+    import torch
+
+    out = np.empty(tuple(dev_tensor.shape), dtype={torch.float32: np.float32, torch.int64: np.int64}[dev_tensor.dtype])
+    _download_into(out, dev_tensor)
+    return out
 
 
 def search(embeddings: np.ndarray, hits: int = 10, metric: int = METRIC_INNER_PRODUCT, device: int | None = None,
@@ -53,7 +122,7 @@ def search(embeddings: np.ndarray, hits: int = 10, metric: int = METRIC_INNER_PR
         index.reset()
     index.add(x)
     scores, results = index.search(x, hits + 1)
-    scores, results = scores.cpu().numpy(), results.cpu().numpy()
+    scores, results = _to_host(scores), _to_host(results)
     # Remove the self hit (blindly column 0, like cath/search.py:26)
     return results[:, 1:], scores[:, 1:]
 
@@ -107,7 +176,7 @@ def faiss_search(haystack, queries: np.ndarray, hits: int = 13, metric: int = ME
     torch.cuda.synchronize(device)
     start = time.time()
     scores, result = index.search(q, hits)
-    scores, result = scores.cpu().numpy(), result.cpu().numpy()
+    scores, result = _to_host(scores), _to_host(result)
     search_time = time.time() - start
     return result, scores, search_time
 
@@ -116,9 +185,7 @@ def _write_back(host: np.ndarray, dev) -> None:
     """faiss.normalize_L2 mutates the caller's float32 C-contiguous array; anything else it refuses."""
     if host.dtype != np.float32 or not host.flags.c_contiguous:
         raise TypeError("normalize_L2 expects a C-contiguous float32 array (it normalises in place)")
-    import torch
-
-    torch.from_numpy(host).copy_(dev)  # device -> the caller's memory directly (no intermediate host copy)
+    _download_into(host, dev)  # device -> the caller's memory directly (no intermediate host array)
 
 
 def proteins_search(full_sequences_data: Path, index_mode: str = "flat", k: int = 1000, device: int | None = None):
@@ -142,7 +209,7 @@ def proteins_search(full_sequences_data: Path, index_mode: str = "flat", k: int 
     write_index(index, str(index_file))
     start = time.time()
     flat_scores, flat_hits = index.search(x, k)
-    flat_scores, flat_hits = flat_scores.cpu().numpy(), flat_hits.cpu().numpy()
+    flat_scores, flat_hits = _to_host(flat_scores), _to_host(flat_hits)
     print(f"Search took {int(time.time() - start)}s")
     np.save(full_sequences_data.joinpath(f"full_sequences_{index_mode}_scores.npy"), flat_scores)
     np.save(full_sequences_data.joinpath(f"full_sequences_{index_mode}_hits.npy"), flat_hits)
