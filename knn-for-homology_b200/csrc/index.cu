@@ -17,6 +17,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -38,14 +39,58 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Large workspaces (candidate lists: ~1 GB per index) outlive the index that allocated them in a small per-device
+// pool: the reference's drivers build a NEW index per embedding matrix (cath/search.py:20 inside a loop over ~20
+// files and 2 metrics), and a cudaMalloc + cudaFree of a gigabyte per call costs more than the search of a CATH-sized
+// matrix (measured: 13 ms vs up to 175 ms per cath.search.search call depending on the box's allocator state).
+struct WorkspacePool {
+    struct Entry { void* p; size_t bytes; int device; };
+    std::mutex mu;
+    std::vector<Entry> free_list;
+    size_t pooled = 0;
+    static constexpr size_t kMinBytes = size_t(32) << 20, kMaxPooled = size_t(6) << 30;
+    void* take(size_t want, int device, size_t* got) {
+        std::lock_guard<std::mutex> g(mu);
+        size_t best = free_list.size();
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].device == device && free_list[i].bytes >= want && free_list[i].bytes <= want + want / 2 &&
+                (best == free_list.size() || free_list[i].bytes < free_list[best].bytes))
+                best = i;
+        if (best == free_list.size()) return nullptr;
+        Entry e = free_list[best];
+        free_list.erase(free_list.begin() + long(best));
+        pooled -= e.bytes;
+        *got = e.bytes;
+        return e.p;
+    }
+    bool give(void* p, size_t bytes, int device) {
+        if (bytes < kMinBytes) return false;
+        std::lock_guard<std::mutex> g(mu);
+        if (pooled + bytes > kMaxPooled) return false;
+        free_list.push_back({p, bytes, device});
+        pooled += bytes;
+        return true;
+    }
+};
+static WorkspacePool g_pool;
+static WorkspacePool g_pinned_pool;  // page-locked bounce buffers (device = -1)
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     int ensure(size_t want) {
         if (want <= bytes) return KNN_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
+        release();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (want >= WorkspacePool::kMinBytes) {
+            size_t got = 0;
+            if (void* q = g_pool.take(want, dev, &got)) {
+                p = q;
+                bytes = got;
+                return KNN_OK;
+            }
+        }
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -55,8 +100,15 @@ struct DevBuf {
         bytes = want;
         return KNN_OK;
     }
+    // Callers release only when no work that touches the buffer is in flight (index destruction synchronises first;
+    // growth happens between searches), so a pooled buffer can be handed to the next owner immediately.
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (bytes >= WorkspacePool::kMinBytes) cudaDeviceSynchronize();  // what cudaFree would have implied
+            if (!g_pool.give(p, bytes, dev)) cudaFree(p);
+        }
         p = nullptr;
         bytes = 0;
     }
@@ -69,6 +121,14 @@ struct PinBuf {  // page-locked host memory (bounce buffers of the host-pointer 
     int ensure(size_t want) {
         if (want <= bytes) return KNN_OK;
         release();
+        if (want >= WorkspacePool::kMinBytes) {
+            size_t got = 0;
+            if (void* q = g_pinned_pool.take(want, -1, &got)) {
+                p = q;
+                bytes = got;
+                return KNN_OK;
+            }
+        }
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -80,7 +140,10 @@ struct PinBuf {  // page-locked host memory (bounce buffers of the host-pointer 
         return KNN_OK;
     }
     void release() {
-        if (p) cudaFreeHost(p);
+        if (p) {
+            if (bytes >= WorkspacePool::kMinBytes) cudaDeviceSynchronize();
+            if (!g_pinned_pool.give(p, bytes, -1)) cudaFreeHost(p);
+        }
         p = nullptr;
         bytes = 0;
     }

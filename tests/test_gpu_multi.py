@@ -99,6 +99,24 @@ def _worker(rank, world, port, out_dir):
         assert torch.equal(I, I1) and torch.equal(D, D1), (rank, "large case")
     assert "exchange_finish_exposed" in index.last_phases_ms
     index.close()
+    # query groups x row shards (bench.py's default layout when the database fits): Q = world (pure query sharding) and,
+    # with 4 GPUs, 2 x 2; speed-weighted query slices; CUDA, pinned-host and numpy queries
+    from knn_b200.distributed import GridIndexFlat, choose_query_groups
+
+    assert choose_query_groups(world, 10_000_000, 1024, 6, device=rank) == world  # C4 fits every B200
+    assert choose_query_groups(8, 100_000_000, 1024, 2, device=rank) == 4         # C5 (205 GB in bf16) needs 2 row shards
+    for Q in sorted({world, 2}):
+        grid = GridIndexFlat(1024, 0, query_groups=Q, device=rank, shard_weights=weights)
+        grid.add(xb2)
+        assert grid.ntotal == 300_000
+        D, I = grid.search(xq2, 100)
+        assert torch.equal(I, I1) and torch.equal(D, D1), (rank, "grid", Q)
+        xq_pinned = torch.empty(xq2.shape, dtype=torch.float32, pin_memory=True).copy_(xq2)
+        D, I = grid.search(xq_pinned, 100)
+        assert D.is_cuda and torch.equal(I, I1) and torch.equal(D, D1), (rank, "grid pinned", Q)
+        Dn, In = grid.search(xq2[:5000].cpu().numpy(), 100)
+        assert isinstance(Dn, np.ndarray) and np.array_equal(In, I1[:5000].cpu().numpy()) and np.array_equal(Dn, D1[:5000].cpu().numpy())
+        grid.close()
     dist.barrier()
     if rank == 0:
         (Path(out_dir) / "ok").write_text(repr(log))
