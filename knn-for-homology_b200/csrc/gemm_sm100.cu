@@ -112,6 +112,16 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
+// Multicast form: the box lands at the same shared-memory offset in every CTA of `mask`, and each destination's bytes
+// are accounted on the barrier (same offset, peer bit cleared) of the LEADER of that destination's CTA pair.
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask,
+                                                    uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -178,13 +188,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // arrives on the mbarrier (CG = 2: on the barrier at this offset in BOTH CTAs of the pair) once all
 // MMAs issued so far by this thread have completed
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t mask = 3) {
     if constexpr (CG == 1) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-    } else {
+    } else {  // arrives on the barrier at this offset in every CTA of `mask` (default: the two CTAs of a lone pair)
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                          smem_u32(bar)),
-                     "h"(uint16_t(3))
+                     "h"(mask)
                      : "memory");
     }
 }
@@ -574,9 +584,19 @@ static size_t stream_smem_bytes(int nq_cta, int num_kb, int stages) {
 // for NQT = 64): the pair's tensor cores read both halves of the N operand, so 128 queries cost no more shared memory
 // per SM than 64 - and the launch stays a pure stream of database bytes where the main kernel would pad the batch to
 // a 256-query tile pair and re-load the query tile with every stage.
-template <int NQT, bool L2, bool DENSE, int CG>
+//
+// NP = 2 (NQT = 128 per pair, 256 queries in all): a cluster of FOUR CTAs = two such pairs on the SAME 256 database
+// rows, pair p scoring queries [128 p, 128 p + 128).  The database half-tile a CTA needs is the one its counterpart
+// in the other pair needs (ranks {0, 2} rows 0..127, ranks {1, 3} rows 128..255), so each of the two loads half of it
+// (64 rows) and TMA-multicasts it to both: the rows cross HBM and L2 once for 256 queries, every SM still does the MMA
+// work of a 128-query launch, and no query tile is ever re-loaded - where the main kernel, for 129..256 queries, keeps
+// the tensor pipe 98 % busy, re-loads its query tile with every stage and runs into the power cap.
+// A stage slot may be refilled once BOTH pairs have consumed it (the refill writes into both), hence empty barriers
+// that count one commit per pair, multicast to all four CTAs.
+template <int NQT, bool L2, bool DENSE, int CG, int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
+    static_assert(NP == 1 || CG == 2, "two pairs need CTA pairs");
     constexpr int NQ_CTA = NQT / CG;                 // query rows staged by one CTA
     constexpr uint32_t kTmemColsS = NQT * kStreamAcc < 32 ? 32 : NQT * kStreamAcc;
     extern __shared__ uint8_t smem_raw[];
@@ -590,10 +610,15 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = args.n_tiles;  // tiles of 128 * CG database rows
-    const uint32_t cta_rank = CG == 1 ? 0u : cluster_ctarank();
+    const uint32_t cl_rank = CG == 1 ? 0u : cluster_ctarank();       // rank in the cluster (0..CG * NP - 1)
+    const uint32_t pair = cl_rank >> 1;                               // which CTA pair of the cluster
+    const uint32_t cta_rank = cl_rank & 1u;                           // position inside the pair
     const bool leader = cta_rank == 0;
-    const int unit = CG == 1 ? blockIdx.x : (blockIdx.x >> 1);
-    const int num_units = CG == 1 ? gridDim.x : (gridDim.x >> 1);
+    const int unit = blockIdx.x / (CG * NP);                          // tile-scheduling unit = cluster
+    const int num_units = gridDim.x / (CG * NP);
+    const int q_base = int(pair) * NQT;                               // first query of this pair
+    const uint16_t pair_mask = uint16_t(3u << (2 * pair));           // the two CTAs of this pair
+    const uint16_t all_mask = uint16_t((1u << (CG * NP)) - 1u);     // every CTA of the cluster
     // instruction descriptor: M = 128 * CG, N = NQT
     const uint32_t idesc = (args.idesc & ~((0x3Fu << 17) | (0x1Fu << 24))) | (uint32_t(NQT >> 3) << 17) | (uint32_t((SBM * CG) >> 4) << 24);
 
@@ -602,7 +627,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         prefetch_tmap(&map_db);
         for (int i = 0; i < nstages; ++i) {
             mbar_init(&bars->full[i], 1);
-            mbar_init(&bars->empty[i], 1);
+            mbar_init(&bars->empty[i], NP);  // one commit per pair that reads (a copy of) the slot
         }
         for (int i = 0; i < kStreamAcc; ++i) {
             mbar_init(&bars->acc_full[i], 1);
@@ -612,7 +637,8 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc<CG>(&bars->tmem_base, kTmemColsS);
-    if (threadIdx.x < 128) thr_s[threadIdx.x] = (threadIdx.x < NQT && threadIdx.x < args.nq) ? args.thr[threadIdx.x] : FLT_MAX;
+    if (threadIdx.x < 128)
+        thr_s[threadIdx.x] = (threadIdx.x < NQT && q_base + int(threadIdx.x) < args.nq) ? args.thr[q_base + threadIdx.x] : FLT_MAX;
     tc_fence_before();
     if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
     tc_fence_after();
@@ -628,7 +654,8 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             } else {
                 if (leader) mbar_expect_tx(&bars->queries, uint32_t(args.num_kb) * bytes_q_kb * 2);
                 for (int kb = 0; kb < args.num_kb; ++kb)
-                    tma_load_2d_pair(smem_q + size_t(kb) * bytes_q_kb, &map_q, &bars->queries, kb * BK, int(cta_rank) * NQ_CTA, args.hint_q);
+                    tma_load_2d_pair(smem_q + size_t(kb) * bytes_q_kb, &map_q, &bars->queries, kb * BK, q_base + int(cta_rank) * NQ_CTA,
+                                     args.hint_q);
             }
             int stage = 0;
             uint32_t phase = 0;
@@ -639,9 +666,16 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     if constexpr (CG == 1) {
                         mbar_expect_tx(&bars->full[stage], kStreamBytesA);
                         tma_load_2d(smem_a + size_t(stage) * kStreamBytesA, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
-                    } else {
+                    } else if constexpr (NP == 1) {
                         if (leader) mbar_expect_tx(&bars->full[stage], kStreamBytesA * 2);
                         tma_load_2d_pair(smem_a + size_t(stage) * kStreamBytesA, &map_db, &bars->full[stage], kb * BK, row_db, args.hint_db);
+                    } else {
+                        // this CTA's half (64 rows) of the 128 rows it shares with rank ^ 2, multicast to both; every leader
+                        // expects the 2 x 16 KB that land in its own pair
+                        if (leader) mbar_expect_tx(&bars->full[stage], kStreamBytesA * 2);
+                        tma_load_2d_pair_mc(smem_a + size_t(stage) * kStreamBytesA + size_t(pair) * (kStreamBytesA / 2), &map_db,
+                                            &bars->full[stage], kb * BK, row_db + int(pair) * (SBM / 2),
+                                            uint16_t(0x5u << cta_rank), args.hint_db);
                     }
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
@@ -667,10 +701,10 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         umma_f16<CG>(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit<CG>(&bars->empty[stage]);
+                    umma_commit<CG>(&bars->empty[stage], NP == 1 ? pair_mask : all_mask);
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit<CG>(&bars->acc_full[acc]);
+                umma_commit<CG>(&bars->acc_full[acc], pair_mask);
                 if (++acc == kStreamAcc) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -678,7 +712,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         // ===== epilogue: warp w owns database rows 32 w .. 32 w + 31 of this CTA's half of the tile (TMEM lanes) =====
         int acc = 0;
         uint32_t acc_phase = 0;
-        const int nq = int(args.nq < NQT ? args.nq : NQT);
+        const int nq = int(args.nq - q_base < NQT ? (args.nq - q_base < 0 ? 0 : args.nq - q_base) : NQT);  // real queries of this pair
         for (int tile = unit; tile < num_tiles; tile += num_units) {
             const int64_t j = args.j0 + int64_t(tile) * (SBM * CG) + int64_t(cta_rank) * SBM + warp * 32 + lane;  // this thread's database row
             const bool row_ok = j < args.j1;
@@ -699,8 +733,8 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                             if (c0 + i < nq) {  // lanes of a warp hold consecutive rows: coalesced per query
                                 float v = __uint_as_float(r[i]);
                                 if (L2) v = 2.0f * v - yn;
-                                args.cand_scores[int64_t(c0 + i) * args.cap + (j - args.j0)] = v;
-                                args.cand_ids[int64_t(c0 + i) * args.cap + (j - args.j0)] = uint32_t(j);
+                                args.cand_scores[int64_t(q_base + c0 + i) * args.cap + (j - args.j0)] = v;
+                                args.cand_ids[int64_t(q_base + c0 + i) * args.cap + (j - args.j0)] = uint32_t(j);
                             }
                         }
                     } else {
@@ -718,7 +752,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                             float v = 0.f;
 #pragma unroll
                             for (int u = 0; u < 32; ++u) v = (u == i) ? __uint_as_float(r[u]) : v;  // no dynamic register indexing
-                            const int64_t q = c0 + i;
+                            const int64_t q = q_base + c0 + i;
                             const int pos = atomicAdd(args.counts + q, 1);
                             if (pos < args.cap) {
                                 args.cand_scores[q * int64_t(args.cap) + pos] = v;
@@ -733,7 +767,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             __syncwarp();
             if (lane == 0) {
                 if constexpr (CG == 1) mbar_arrive(&bars->acc_empty[acc]);
-                else mbar_arrive_remote(&bars->acc_empty[acc], 0);
+                else mbar_arrive_remote(&bars->acc_empty[acc], pair * 2);  // the leader of this pair
             }
             if (++acc == kStreamAcc) { acc = 0; acc_phase ^= 1; }
         }
@@ -762,6 +796,7 @@ struct GemmPlan {
     int stages = 0;     // 0: default depth (4)
     int stream_kernel = 1;  // launches with <= 64 queries use the few-queries variant (database rows as the M operand)
     int stream_pair = 1;    // launches with 65..128 queries use the CTA-pair form of the few-queries variant
+    int stream_quad = 1;    // launches with 129..256 queries use its two-pair (cluster of 4, multicast) form
     int small_m128 = 0;     // experiments: launches with 65..128 queries use the single-CTA (M = 128) variant of the main kernel
 };
 
@@ -772,6 +807,7 @@ void gemm_plan_set_stages(GemmPlan* p, int stages) { p->stages = stages; }
 void gemm_plan_set_stream_kernel(GemmPlan* p, int on) { p->stream_kernel = on; }
 void gemm_plan_set_small_m128(GemmPlan* p, int on) { p->small_m128 = on; }
 void gemm_plan_set_stream_pair(GemmPlan* p, int on) { p->stream_pair = on; }
+void gemm_plan_set_stream_quad(GemmPlan* p, int on) { p->stream_quad = on; }
 int gemm_plan_query_rows_multiple(const GemmPlan* p) { return BM * p->cta_group; }
 
 int gemm_plan_create(GemmPlan** out, int device) {
@@ -853,10 +889,10 @@ static int launch_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorM
     return KNN_OK;
 }
 
-template <int NQT, bool L2, bool DENSE, int CG>
+template <int NQT, bool L2, bool DENSE, int CG, int NP = 1>
 static int launch_stream_variant(GemmPlan* p, const CUtensorMap& map_q, const CUtensorMap& map_db, const GemmArgs& a, size_t smem,
                                  cudaStream_t s) {
-    auto kern = gemm_stream_kernel<NQT, L2, DENSE, CG>;
+    auto kern = gemm_stream_kernel<NQT, L2, DENSE, CG, NP>;
     static bool attr_done[64] = {};
     int dev = 0;
     KNN_CHECK_CUDA(cudaGetDevice(&dev));
@@ -864,20 +900,30 @@ static int launch_stream_variant(GemmPlan* p, const CUtensorMap& map_q, const CU
         KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    const int units_max = p->sms / CG;
-    const int units = a.n_tiles < units_max ? a.n_tiles : units_max;
+    int units_max = p->sms / (CG * NP);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(units * CG), 1, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CG * NP;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (NP > 1) {  // clusters of 4 must fit inside a GPC: ask how many can be resident at once (persistent grid)
+        static int max_clusters[64] = {};
+        if (dev >= 0 && dev < 64 && !max_clusters[dev]) {
+            cfg.gridDim = dim3(unsigned(units_max * CG * NP), 1, 1);
+            int n = 0;
+            KNN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+            max_clusters[dev] = n > 0 ? n : 1;
+        }
+        if (dev >= 0 && dev < 64 && max_clusters[dev] < units_max) units_max = max_clusters[dev];
+    }
+    const int units = a.n_tiles < units_max ? a.n_tiles : units_max;
+    cfg.gridDim = dim3(unsigned(units * CG * NP), 1, 1);
     KNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_q, map_db, a));
     KNN_CHECK_LAUNCH();
     return KNN_OK;
@@ -888,8 +934,10 @@ static int try_stream_launch(GemmPlan* p, const h16_t* xq_h16, int fmt, int64_t 
                              int64_t ntotal, const float* ynorm2, int64_t j0, int64_t j1, int metric, bool dense_first,
                              FilterState st, cudaStream_t s, bool* done) {
     *done = false;
-    if (!p->stream_kernel || nq > 128 || nq_pad < 128 || dp % BK != 0) return KNN_OK;
+    if (!p->stream_kernel || nq > 256 || nq_pad < 256 || dp % BK != 0) return KNN_OK;
     if (nq > 64 && !p->stream_pair) return KNN_OK;
+    if (nq > 128 && !p->stream_quad) return KNN_OK;
+    const int np = nq > 128 ? 2 : 1;    // 129..256 queries: two CTA pairs per cluster, 128 queries each
     const int nqt = nq <= 32 ? 32 : (nq <= 64 ? 64 : 128);
     const int cg = nqt == 128 ? 2 : 1;  // 128 queries: a CTA pair, each CTA keeps 64 of them resident
     const int nq_cta = nqt / cg;
@@ -899,7 +947,7 @@ static int try_stream_launch(GemmPlan* p, const h16_t* xq_h16, int fmt, int64_t 
     if (stages < 4) return KNN_OK;  // the resident queries leave no room for a ring: the main kernel takes it
     CUtensorMap map_q, map_db;
     KNN_CHECK(make_map(p, &map_q, xq_h16, nq_pad, dp, nq_cta));
-    KNN_CHECK(make_map(p, &map_db, xb_h16, ntotal, dp, SBM));
+    KNN_CHECK(make_map(p, &map_db, xb_h16, ntotal, dp, np == 2 ? SBM / 2 : SBM));  // two pairs: each CTA loads half of its rows
     GemmArgs a;
     a.nq = nq;
     a.m_tiles = 1;
@@ -928,6 +976,14 @@ static int try_stream_launch(GemmPlan* p, const h16_t* xq_h16, int fmt, int64_t 
     } else {                                                                                                           \
         return dense_first ? launch_stream_variant<NQTV, false, true, CGV>(p, map_q, map_db, a, smem, s)               \
                            : launch_stream_variant<NQTV, false, false, CGV>(p, map_q, map_db, a, smem, s);             \
+    }
+    if (np == 2) {
+        if (l2) {
+            return dense_first ? launch_stream_variant<128, true, true, 2, 2>(p, map_q, map_db, a, smem, s)
+                               : launch_stream_variant<128, true, false, 2, 2>(p, map_q, map_db, a, smem, s);
+        }
+        return dense_first ? launch_stream_variant<128, false, true, 2, 2>(p, map_q, map_db, a, smem, s)
+                           : launch_stream_variant<128, false, false, 2, 2>(p, map_q, map_db, a, smem, s);
     }
     if (nqt == 32) { KNN_STREAM_DISPATCH(32, 1) } else if (nqt == 64) { KNN_STREAM_DISPATCH(64, 1) } else { KNN_STREAM_DISPATCH(128, 2) }
 #undef KNN_STREAM_DISPATCH

@@ -245,6 +245,7 @@ struct knn_index {
     int gemm_stages = 0;
     int stream_kernel = 1;
     int stream_pair = 1;
+    int stream_quad = 1;
     int l2_blocked_rerank = 0;  // opt-in: cuts the rerank's DRAM bytes 10 x but is 2 x slower (see kernels_basic.cu)
     int small_m128 = 0;  // measured slower than the CTA-pair tiles (5.9 vs 4.6 ms at 128 queries x 10M rows): off
     int panel_ratio = 0;  // 0: automatic
@@ -490,6 +491,7 @@ int tensor_prepare(knn_index* ix) {
     gemm_plan_set_stream_kernel(ix->plan, ix->stream_kernel);
     gemm_plan_set_small_m128(ix->plan, ix->small_m128);
     gemm_plan_set_stream_pair(ix->plan, ix->stream_pair);
+    gemm_plan_set_stream_quad(ix->plan, ix->stream_quad);
     return KNN_OK;
 }
 
@@ -1399,6 +1401,7 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "overlap_finish") ix->overlap_finish = value != 0;
     else if (n == "small_m128") ix->small_m128 = value != 0;
     else if (n == "stream_pair") ix->stream_pair = value != 0;
+    else if (n == "stream_quad") ix->stream_quad = value != 0;
     else if (n == "l2_blocked_rerank") ix->l2_blocked_rerank = value != 0;
     else if (n == "split_single_batch") ix->split_single_batch = value != 0;
     else if (n == "panel_ratio" && value >= 0 && value <= 64) ix->panel_ratio = int(value);

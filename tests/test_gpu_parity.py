@@ -368,11 +368,13 @@ def test_bf16_storage_index(knn):
 @pytest.mark.parametrize("metric", [IP, L2])
 @pytest.mark.parametrize("nq,nb,d,k", [(1, 20000, 1024, 100), (17, 9000, 96, 10), (32, 30000, 256, 1000), (33, 12345, 1024, 5),
                                        (64, 50000, 512, 200), (5, 8192, 1900, 13), (40, 8192, 1900, 13), (64, 70000, 64, 2048),
-                                       (65, 33333, 1024, 100), (128, 60001, 1024, 10), (100, 9000, 320, 1000), (127, 20000, 1900, 50)])
+                                       (65, 33333, 1024, 100), (128, 60001, 1024, 10), (100, 9000, 320, 1000), (127, 20000, 1900, 50),
+                                       (129, 40000, 1024, 100), (256, 70001, 1024, 10), (200, 9000, 320, 1000), (255, 30011, 512, 64)])
 def test_few_queries_stream_kernel(knn, nq, nb, d, k, metric):
     """Launches with <= 64 queries take the few-queries variant of the GEMM kernel (database rows as the M operand,
     queries resident in shared memory) unless the resident queries leave no room for the ring (d = 1900, nq > 32);
-    65..128 queries take its CTA-pair form (tcgen05 cta_group::2, each CTA of the pair keeps half of the queries).
+    65..128 queries take its CTA-pair form (tcgen05 cta_group::2, each CTA of the pair keeps half of the queries),
+    129..256 its two-pair form (cluster of 4, database half-tiles TMA-multicast to both pairs).
     Same bits as the main kernel and as the exact scan, both operand formats, dense first panel included."""
     xq, xb = _data(nq, nb, d, seed=nq * 7 + d, normalize=metric == IP, scale=1.3)
     D1, I1, _ = _search(knn, xq, xb, k, metric, path=1)
