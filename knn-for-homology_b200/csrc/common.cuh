@@ -183,7 +183,7 @@ void gemm_plan_set_debug(GemmPlan* p, int skip_epilogue);
 void gemm_plan_set_stages(GemmPlan* p, int stages);
 void gemm_plan_set_stream_kernel(GemmPlan* p, int on);   // few-queries variant for launches with <= 64 queries (default on)
 void gemm_plan_set_stream_pair(GemmPlan* p, int on);     // 65..128 queries: CTA-pair form of the few-queries variant (default on)
-void gemm_plan_set_stream_quad(GemmPlan* p, int on);     // 129..256 queries: two pairs per cluster, database tiles multicast (default on)
+void gemm_plan_set_stream_quad(GemmPlan* p, int on);     // experiments: 129..256 queries on two pairs per cluster, database tiles multicast (default off)
 void gemm_plan_set_small_m128(GemmPlan* p, int on);      // 65..128 queries: single-CTA (M = 128) tiles (default on)
 int gemm_plan_query_rows_multiple(const GemmPlan* p);     // nq_pad granularity of the chosen variant
 // Scores queries (16-bit, format fmt_q, [nq_pad x dp]) against database rows [j0, j1) (16-bit, format fmt_db,

@@ -593,6 +593,13 @@ static size_t stream_smem_bytes(int nq_cta, int num_kb, int stages) {
 // the tensor pipe 98 % busy, re-loads its query tile with every stage and runs into the power cap.
 // A stage slot may be refilled once BOTH pairs have consumed it (the refill writes into both), hence empty barriers
 // that count one commit per pair, multicast to all four CTAs.
+// MEASURED (256 queries x 10M rows, whole call): correct (bit-identical, tests/test_gpu_parity.py), but 7.4 ms against
+// the main kernel's 6.0 ms - and the arithmetic says why no form of it can reach the HBM roof: a cluster RECEIVES
+// 64 KB per K block for 32 KB of unique rows, so streaming unique rows at HBM speed needs every SM to take a 16 KB
+// stage per 0.19 us, exactly the time its MMAs for that stage take at the full clock.  256 queries are the machine
+// balance; under the power cap (1.3-1.4 GHz) the tensor pipe sets the pace, and the multicast loads' longer latency on a
+// 6-stage ring costs the rest.  Off by default ("stream_quad"); kept because it is the measured answer to "would
+// multicast help".
 template <int NQT, bool L2, bool DENSE, int CG, int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const GemmArgs args) {
@@ -796,7 +803,7 @@ struct GemmPlan {
     int stages = 0;     // 0: default depth (4)
     int stream_kernel = 1;  // launches with <= 64 queries use the few-queries variant (database rows as the M operand)
     int stream_pair = 1;    // launches with 65..128 queries use the CTA-pair form of the few-queries variant
-    int stream_quad = 1;    // launches with 129..256 queries use its two-pair (cluster of 4, multicast) form
+    int stream_quad = 0;    // experiments: 129..256 queries on its two-pair (cluster of 4, multicast) form - measured slower
     int small_m128 = 0;     // experiments: launches with 65..128 queries use the single-CTA (M = 128) variant of the main kernel
 };
 

@@ -245,7 +245,7 @@ struct knn_index {
     int gemm_stages = 0;
     int stream_kernel = 1;
     int stream_pair = 1;
-    int stream_quad = 1;
+    int stream_quad = 0;  // measured: 7.4 ms against the main kernel's 6.0 ms at 256 queries x 10M rows (gemm_sm100.cu)
     int l2_blocked_rerank = 0;  // opt-in: cuts the rerank's DRAM bytes 10 x but is 2 x slower (see kernels_basic.cu)
     int small_m128 = 0;  // measured slower than the CTA-pair tiles (5.9 vs 4.6 ms at 128 queries x 10M rows): off
     int panel_ratio = 0;  // 0: automatic

@@ -380,7 +380,9 @@ def test_few_queries_stream_kernel(knn, nq, nb, d, k, metric):
     D1, I1, _ = _search(knn, xq, xb, k, metric, path=1)
     for fmt in (BF16, FP16):
         for stream in (1, 0):
-            D, I, idx = _search(knn, xq, xb, k, metric, path=2, shadow_fmt=fmt, stream_kernel=stream)
+            # stream_quad: the two-pair (cluster of 4, TMA multicast) form for 129..256 queries - off by default
+            # (measured slower than the main kernel), exercised here so that it stays correct
+            D, I, idx = _search(knn, xq, xb, k, metric, path=2, shadow_fmt=fmt, stream_kernel=stream, stream_quad=stream)
             assert idx.stat("path") == 2 and idx.stat("overflow_batches") == 0
             assert np.array_equal(I, I1) and np.array_equal(D, D1), (fmt, stream)
     D_ref, I_ref = fo.knn_flat(xq, xb, k, metric, want=k + 4)  # + the next candidates: k-boundary rule
