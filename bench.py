@@ -550,6 +550,8 @@ def main():
                                 "ranks and answers 1/Q of the queries; chosen as the largest group count whose row share fits 60 % of the "
                                 "GPU memory unless --query-groups says otherwise (1 = plain row sharding)")},
             "rank_speed_weights": [round(w, 4) for w in weights] if weights else None,
+            "query_share_by_group": ([round(w / sum(index.group_weights), 4) for w in index.group_weights]
+                                     if Q > 1 and getattr(index, "group_weights", None) else None),
             "overlap_finish": not args.no_overlap, "params": args.param or None,
         }
         print(json.dumps(line), flush=True)
