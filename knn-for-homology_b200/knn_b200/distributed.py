@@ -652,14 +652,19 @@ class GridIndexFlat:
         col_groups = [dist.new_group([g * self.R + r for g in range(self.Q)]) for r in range(self.R)]
         self.col_group = col_groups[self.r]
         self.group_weights = None  # share of the queries every group takes (None: equal shares)
-        # The first `autotune_calls` large searches re-balance the query slices from the groups' own measured times: a
-        # call ends when the slowest group is done, the chips of one box do not clock alike under the board power cap,
-        # and a 2 s calibration on a small database (measured_rank_speeds) leaves ~2 % of spread on the real workload
-        # (8 B200, C4: GEMM 171.5-175.9 ms per rank).  Each tuning call costs one host synchronisation; results never
-        # depend on the slices (ids are global, every query is answered by one whole group).
-        self.autotune_calls = 3
+        # Large searches re-balance the query slices from the groups' own measured times: a call ends when the slowest
+        # group is done, the chips of one box do not clock alike under the board power cap, and a 2 s calibration on a
+        # small database (measured_rank_speeds) leaves ~2 % of spread on the real workload (8 B200, C4: GEMM 171.5-175.9
+        # ms per rank).  Every large call is bracketed by two CUDA events (no synchronisation); at call numbers 2, 4, 8,
+        # 16, ... the PREVIOUS call's time - taken back to back with its neighbours, i.e. in the power state the chips
+        # really run in; a first version that tuned on synchronised calls measured the wrong (cool) state and left the
+        # spread where it was - is all-gathered and the shares move towards the measured rates.  That costs one host
+        # synchronisation per tuning point; results never depend on the slices (ids are global, every query is answered
+        # by one whole group).
+        self.autotune = True
         self.autotune_min_queries = 8192
-        self.tuned_calls = 0
+        self._calls = 0
+        self._last = None  # (t0, t1, per-group query counts) of the previous large call
         if shard_weights is not None:  # one weight per rank of the world
             w = list(shard_weights)
             # a group is as fast as its ranks together (its row shards are already sized by their weights)
@@ -706,20 +711,25 @@ class GridIndexFlat:
 
         as_numpy = isinstance(x, np.ndarray)
         n = x.shape[0]
-        lo, hi = self.query_slice(n)
         on_cuda = self._dist.get_backend(self.col_group) == "nccl"
+        timed_call = on_cuda and self.Q > 1 and self.autotune and n >= self.autotune_min_queries
+        if timed_call:
+            self._calls += 1
+            if self._last is not None and self._calls >= 2 and (self._calls & (self._calls - 1)) == 0:
+                self._retune(*self._last)  # the shares move before this call is sliced
+        lo, hi = self.query_slice(n)
         xs = x[lo:hi]
         if on_cuda and (as_numpy or not xs.is_cuda):
             # host queries: only this group's slice crosses PCIe (its ranks share the upload), results stay on the device
             xs = self.inner.upload_queries(xs)
-        tune = (on_cuda and self.Q > 1 and self.tuned_calls < self.autotune_calls and n >= self.autotune_min_queries)
-        if tune:
+        if timed_call:
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
         D, I = self.inner.search(xs, k)
-        if tune:
+        if timed_call:
             t1.record()
-            self._retune(t0, t1, n)
+            b_now = self.query_bounds(n)
+            self._last = (t0, t1, [b_now[g + 1] - b_now[g] for g in range(self.Q)])
         if self.Q == 1:
             return (_to_numpy(D), _to_numpy(I)) if as_numpy and not isinstance(D, np.ndarray) else (D, I)
         if isinstance(D, np.ndarray):
@@ -739,9 +749,9 @@ class GridIndexFlat:
             return _to_numpy(D), _to_numpy(I)
         return D, I
 
-    def _retune(self, t0, t1, n: int) -> None:
-        """Collective over the world: every group's time for its slice of this call -> new query shares, proportional to
-        the measured rates (damped), identical on every rank."""
+    def _retune(self, t0, t1, counts) -> None:
+        """Collective over the world: every group's time for its slice of the measured call -> new query shares,
+        moved towards the measured rates (damped), identical on every rank."""
         import torch
 
         t1.synchronize()
@@ -750,9 +760,7 @@ class GridIndexFlat:
         times = torch.zeros(world, dtype=torch.float64, device=mine.device)
         self._dist.all_gather_into_tensor(times, mine)
         times = times.tolist()
-        b = self.query_bounds(n)
         group_ms = [max(times[g * self.R:(g + 1) * self.R]) for g in range(self.Q)]
-        counts = [b[g + 1] - b[g] for g in range(self.Q)]
         if min(group_ms) <= 0 or min(counts) <= 0:
             return
         rates = [c / t for c, t in zip(counts, group_ms)]          # queries per ms, as measured on this workload
@@ -760,7 +768,6 @@ class GridIndexFlat:
         so, sr = sum(old), sum(rates)
         new = [0.3 * o / so + 0.7 * r / sr for o, r in zip(old, rates)]  # damped: one noisy call cannot swing the split
         self.group_weights = [w * self.Q / sum(new) for w in new]
-        self.tuned_calls += 1
 
     def close(self) -> None:
         self.inner.close()
