@@ -72,6 +72,7 @@ def parse():
                     help="c4 (default): 10M x 1024, 100k queries, k=100.  c2: CATH20 stand-in, 14433 all-vs-all, k=1000.  "
                          "c3: Pfam20 stand-in, 300k all-vs-all, k=1000.  c5: 100M bf16 rows, 1M queries, k=1000 (8 GPUs)")
     ap.add_argument("--no-small-batch", action="store_true", help="N = 1: skip the small-batch (HBM roofline) legs")
+    ap.add_argument("--no-autotune", action="store_true", help="query groups: keep the calibrated query shares (no feedback from measured call times)")
     ap.add_argument("--no-overlap", action="store_true", help="finish phase of a batch on the main stream (no side stream)")
     ap.add_argument("--parity-queries", type=int, default=256)
     ap.add_argument("--param", action="append", default=[], metavar="NAME=VALUE",
@@ -326,6 +327,8 @@ def main():
                                  shard_weights=weights)
         b = shard_bounds(args.nb, world, weights)
         lo, hi = b[rank], b[rank + 1]
+    if Q > 1 and args.no_autotune:
+        index.autotune = False
     index.local.set_param("cta_group", args.cta_group)
     if args.shadow_fmt and not args.bf16_storage:
         index.local.set_param("shadow_fmt", args.shadow_fmt)
@@ -552,7 +555,7 @@ def main():
             "rank_speed_weights": [round(w, 4) for w in weights] if weights else None,
             "query_share_by_group": ([round(w / sum(index.group_weights), 4) for w in index.group_weights]
                                      if Q > 1 and getattr(index, "group_weights", None) else None),
-            "overlap_finish": not args.no_overlap, "params": args.param or None,
+            "overlap_finish": not args.no_overlap, "params": args.param or None, "autotune_query_shares": bool(Q > 1 and not args.no_autotune),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
