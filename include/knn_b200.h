@@ -218,7 +218,10 @@ int knn_prefilter_emit_dev(int64_t nq, int64_t k, const int64_t* I_dev, const fl
  * "overflow_queries"; of the index: "capacity", "shadow_fmt" (1 bf16, 2 fp16), "mantissa_bits",
  * "shadow_conversions" (times the shadow rows were rewritten in the other format).
  * "overlap_finish" (default 1): a search of several query batches runs the exact rescoring of batch b on an internal
- * side stream under the tensor-core filter of batch b + 1. */
+ * side stream under the tensor-core filter of batch b + 1; "split_single_batch" (default 1): a one-batch call with
+ * k >= 256 is cut into up to four batches for the same reason; "stream_pair" (default 1): 65..128 queries on the
+ * CTA-pair form of the few-queries kernel.  Measured-and-rejected variants kept as opt-ins (never change results):
+ * "l2_blocked_rerank", "stream_quad", "small_m128". */
 int knn_index_set_param(knn_index* idx, const char* name, int64_t value);
 int knn_index_get_stat(const knn_index* idx, const char* name, double* out);
 

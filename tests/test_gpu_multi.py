@@ -139,3 +139,57 @@ def test_sharded_two_phase_search_over_nccl_equals_unsharded_and_oracle(tmp_path
             pytest.fail("multi-GPU workers did not finish in 600 s")
     log = (tmp_path / "ok").read_text()
     print("oracle parity over NCCL (metric, k, excused, max_rel_err_D):", log)
+
+
+def test_dev_entry_points_follow_their_pointers_not_the_current_device():
+    """the stateless *_dev entry points (normalize, merge, post-processing) and an index created
+    with device=1 must work while the CALLER's current device is 0 - they select the device that owns the memory they
+    are handed; the SM count is cached per device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    sys.path.insert(0, str(REPO))
+    sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
+    import knn_b200
+    from oracle import flat_oracle as fo
+
+    torch.cuda.set_device(0)
+    rng = np.random.default_rng(3)
+    xb = rng.standard_normal((20000, 128)).astype(np.float32)
+    xq = rng.standard_normal((300, 128)).astype(np.float32)
+    ref_b, ref_q = xb.copy(), xq.copy()
+    fo.normalize_L2(ref_b)
+    fo.normalize_L2(ref_q)
+    dev1 = torch.device("cuda", 1)
+    tb, tq = torch.from_numpy(xb).to(dev1), torch.from_numpy(xq).to(dev1)
+    knn_b200.normalize_L2(tb)           # knn_normalize_l2_dev on cuda:1 memory, current device 0
+    knn_b200.normalize_L2(tq)
+    assert torch.cuda.current_device() == 0
+    np.testing.assert_allclose(tb.cpu().numpy(), ref_b, rtol=2e-6, atol=1e-7)
+    index = knn_b200.IndexFlat(128, 0, device=1)
+    index.set_param("path", 2)
+    index.add(tb)
+    D, I = index.search(tq, 10)
+    single0 = knn_b200.IndexFlat(128, 0, device=0)
+    single0.set_param("path", 2)
+    single0.add(tb.to("cuda:0"))
+    D0, I0 = single0.search(tq.to("cuda:0"), 10)
+    assert D.device == dev1 and torch.equal(I.cpu(), I0.cpu()) and torch.equal(D.cpu(), D0.cpu())
+    # merge of two half-results on cuda:1
+    h = 10000
+    a = knn_b200.IndexFlat(128, 0, device=1)
+    b = knn_b200.IndexFlat(128, 0, device=1)
+    a.add(tb[:h])
+    b.add(tb[h:])
+    Da, Ia = a.search(tq, 10)
+    Db, Ib = b.search(tq, 10, id_base=h)
+    Dm, Im = knn_b200.merge_topk(torch.stack([Da, Db]), torch.stack([Ia, Ib]), 0)
+    assert torch.equal(Im.cpu(), I0.cpu()) and torch.equal(Dm.cpu(), D0.cpu())
+    # post-processing on cuda:1
+    fam_db = rng.integers(0, 40, 20000).astype(np.int32)
+    fam_q = rng.integers(0, 40, 300).astype(np.int32)
+    lead1, tp1, _ = knn_b200.evaluate_ids(I, fam_q, fam_db)
+    lead0, tp0, _ = knn_b200.evaluate_ids(I0, fam_q, fam_db)
+    assert torch.equal(lead1.cpu(), lead0.cpu()) and torch.equal(tp1.cpu(), tp0.cpu())
+    assert torch.cuda.current_device() == 0
