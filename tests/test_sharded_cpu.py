@@ -165,3 +165,23 @@ def test_grid_index_world4_gloo(tmp_path):
     out = tmp_path / "ok"
     mp.spawn(_grid_worker, args=(4, port, str(out)), nprocs=4, join=True)
     assert out.read_text() == "ok"
+
+
+def test_choose_query_groups_by_memory_fit():
+    """Layout rule of the multi-GPU bench: the largest number of query groups whose per-rank
+    share of the rows fits 60 % of the GPU memory (180 GB assumed when no GPU is visible)."""
+    sys.path.insert(0, str(REPO / "knn-for-homology_b200"))
+    from knn_b200.distributed import choose_query_groups, shard_bounds
+
+    if torch.cuda.is_available():
+        pytest.skip("sizes below assume the 180 GB default of a box without a visible GPU")
+    assert choose_query_groups(8, 10_000_000, 1024, 6) == 8       # C4: 61 GB fit every GPU -> pure query sharding
+    assert choose_query_groups(4, 10_000_000, 1024, 6) == 4
+    assert choose_query_groups(8, 100_000_000, 1024, 2) == 4      # C5: 205 GB in bf16 -> two row shards per group
+    assert choose_query_groups(8, 100_000_000, 1024, 6) == 1      # 614 GB with fp32 master rows -> all 8 GPUs per group
+    assert choose_query_groups(6, 30_000_000, 1024, 6) == 3       # divisors of the world only
+    assert choose_query_groups(1, 10, 8, 6) == 1
+    # weighted bounds cover the range exactly and respect the order of the weights
+    b = shard_bounds(100_000, 8, [0.1238, 0.1265, 0.1237, 0.1241, 0.1275, 0.1236, 0.1237, 0.127])
+    assert b[0] == 0 and b[-1] == 100_000 and all(x <= y for x, y in zip(b, b[1:]))
+    assert (b[5] - b[4]) > (b[6] - b[5])
