@@ -156,29 +156,62 @@ def faiss_search(haystack, queries: np.ndarray, hits: int = 13, metric: int = ME
     """seqvec_search/main.py:22-50.  ``haystack`` is a matrix or a ready index.  Returns
     ``(ids, scores, search_seconds)`` - ids first.  Like the reference, queries (and a matrix
     haystack) are L2-normalised IN PLACE for the inner-product metric."""
+    import threading
+
+    import torch
+
     device = _default_device() if device is None else device
     q = _upload(queries, device)
     if metric == METRIC_INNER_PRODUCT:
         normalize_L2(q)
         _write_back(queries, q)
+    writer = None
     if isinstance(haystack, np.ndarray):
         h = _upload(haystack, device)
         if metric == METRIC_INNER_PRODUCT:
             normalize_L2(h)
-            _write_back(haystack, h)
+            if haystack.dtype != np.float32 or not haystack.flags.c_contiguous:
+                raise TypeError("normalize_L2 expects a C-contiguous float32 array (it normalises in place)")
+            # The reference's in-place normalisation has to reach the caller's array (main.py:34), gigabytes over PCIe
+            # that nothing below depends on: they travel on a side stream, driven by a helper thread, while the index
+            # is built and searched, and are home before this function returns.
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(device))
+            writer = threading.Thread(target=_write_back_async, args=(haystack, h, device, ready), daemon=True)
+            writer.start()
         index = IndexFlat(h.shape[1], metric, device=device)
         index.train(h)
         index.add(h)
     else:
         index = haystack
-    import torch
-
-    torch.cuda.synchronize(device)
+    torch.cuda.current_stream(device).synchronize()
     start = time.time()
     scores, result = index.search(q, hits)
+    if writer is not None:  # the bounce buffers are shared: the results travel after the write-back
+        torch.cuda.current_stream(device).synchronize()
+        writer.join()
     scores, result = _to_host(scores), _to_host(result)
-    search_time = time.time() - start
+    search_time = time.time() - start  # like faiss's index.search: until (D, I) are numpy arrays
+    if _write_back_error:
+        raise _write_back_error.pop()
     return result, scores, search_time
+
+
+_write_back_error = []
+
+
+def _write_back_async(host: np.ndarray, dev, device: int, ready) -> None:
+    import torch
+
+    try:
+        torch.cuda.set_device(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            _download_into(host, dev)
+        side.synchronize()
+    except Exception as e:  # surfaced by the caller
+        _write_back_error.append(e)
 
 
 def _write_back(host: np.ndarray, dev) -> None:
