@@ -683,7 +683,9 @@ int launch_tighten(FilterState st, const float* eps, int64_t nq, int k, int comp
                    cudaStream_t s) {
     (void)tau_out;
     if (nq <= 0) return KNN_OK;
-    if (k <= 256 && compact) {
+    // One warp per query needs thousands of queries to fill the GPU; a small batch (<= 512 queries) is latency-bound in
+    // its bit-by-bit search, so it takes the block-per-query kernel (radix passes by 256 threads) whatever k is.
+    if (k <= 256 && compact && nq > 512) {
         tighten_warp_kernel<<<unsigned((nq + 7) / 8), 256, 0, s>>>(st.thr, st.counts, st.cand_scores, st.cand_ids, st.cap,
                                                                    eps, nq, k, overflow, st.ovf);
     } else {
