@@ -1079,18 +1079,27 @@ int knn_index_add(knn_index* ix, int64_t n, const float* x) {
     KNN_CHECK(ix->stage.ensure(stage_bytes));
     if (n > rows_per) KNN_CHECK(ix->stage2.ensure(stage_bytes));
     int64_t c = 0;
-    for (int64_t r0 = 0; r0 < n; r0 += rows_per, ++c) {
-        const int64_t nr = n - r0 < rows_per ? n - r0 : rows_per;
-        const int w = int(c & 1);
-        float* st = (w ? ix->stage2 : ix->stage).as<float>();
-        if (c >= 2) KNN_CHECK_CUDA(cudaEventSynchronize(ix->stage_free[w]));  // the ingest that read this buffer is done
-        KNN_CHECK_CUDA(cudaMemcpyAsync(st, x + r0 * ix->d, size_t(nr) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->copy_in));
-        KNN_CHECK_CUDA(cudaEventRecord(ix->hp_in_ready[w], ix->copy_in));
-        KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->stream, ix->hp_in_ready[w], 0));
-        KNN_CHECK(knn_index_add_dev(ix, nr, st, ix->stream));
-        KNN_CHECK_CUDA(cudaEventRecord(ix->stage_free[w], ix->stream));
+    auto add_chunks = [&]() -> int {
+        for (int64_t r0 = 0; r0 < n; r0 += rows_per, ++c) {
+            const int64_t nr = n - r0 < rows_per ? n - r0 : rows_per;
+            const int w = int(c & 1);
+            float* st = (w ? ix->stage2 : ix->stage).as<float>();
+            if (c >= 2) KNN_CHECK_CUDA(cudaEventSynchronize(ix->stage_free[w]));  // the ingest that read this buffer is done
+            KNN_CHECK_CUDA(cudaMemcpyAsync(st, x + r0 * ix->d, size_t(nr) * ix->d * sizeof(float), cudaMemcpyHostToDevice, ix->copy_in));
+            KNN_CHECK_CUDA(cudaEventRecord(ix->hp_in_ready[w], ix->copy_in));
+            KNN_CHECK_CUDA(cudaStreamWaitEvent(ix->stream, ix->hp_in_ready[w], 0));
+            KNN_CHECK(knn_index_add_dev(ix, nr, st, ix->stream));
+            KNN_CHECK_CUDA(cudaEventRecord(ix->stage_free[w], ix->stream));
+        }
+        return KNN_OK;
+    };
+    const int rc = add_chunks();
+    // `add` copies (faiss semantics): the caller may reuse x once this returns - also when it returns an error
+    if (rc != KNN_OK) {
+        cudaDeviceSynchronize();
+        return rc;
     }
-    KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));  // `add` copies (faiss semantics): the caller may reuse x now
+    KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
     return KNN_OK;
 }
 
@@ -1122,7 +1131,13 @@ int knn_index_search(knn_index* ix, int64_t nq, const float* xq, int64_t k, floa
     if (ix->ntotal > 0 && use_tensor_path(ix, nq, int(k))) {
         // tensor path: one pipelined pass over the query batches (copies under compute, see HostPipe)
         HostPipe hp{ix, xq, D, I, int(k), host_pointer_is_pinned(xq), host_pointer_is_pinned(D) && host_pointer_is_pinned(I)};
-        KNN_CHECK(search_dev_impl(ix, nq, xq, k, D, I, 0, ix->stream, &hp));
+        const int rc = search_dev_impl(ix, nq, xq, k, D, I, 0, ix->stream, &hp);
+        if (rc != KNN_OK) {
+            // copies into / out of the caller's arrays may still be in flight on the copy streams: nothing may touch
+            // the caller's memory once this call has returned, error or not
+            cudaDeviceSynchronize();
+            return rc;
+        }
         KNN_CHECK_CUDA(cudaStreamSynchronize(ix->stream));
         return KNN_OK;
     }
