@@ -110,7 +110,8 @@ int knn_index_search_finish_dev(knn_index* idx, int64_t nq, const float* xq_dev,
  *   filter_batch  filters batch b and writes its bounds into bounds_dev, a caller-zeroed float array
  *                 [nbatches][2][batch_rows]: [b][0][i] = lower bound of the k-th best true score of query
  *                 b*batch_rows+i in this shard, [b][1][i] = MINUS the bound on the j-th best (j = ceil(k / shards)):
- *                 ONE element-wise MAX all-reduce of the slice [b] over the shards combines both;
+ *                 ONE element-wise MAX all-reduce of the slice [b] over the shards combines both.  The second bound is
+ *                 only valid AFTER that reduction over all `shards` shards (with a single shard pass j = k);
  *   finish_batch  applies max([b][0], -[b][1]) and writes rows [b*batch_rows, ...) of this shard's (D, I);
  *   end           after every batch has finished (stream-ordered): repairs overflowed queries, closes the search. */
 int knn_index_search_begin_dev(knn_index* idx, int64_t nq, const float* xq_dev, int64_t k, int64_t* nbatches_out,
