@@ -245,6 +245,7 @@ struct knn_index {
     int gemm_stages = 0;
     int stream_kernel = 1;
     int stream_pair = 1;
+    int dense_small_db = 1;
     int stream_quad = 0;  // measured: 7.4 ms against the main kernel's 6.0 ms at 256 queries x 10M rows (gemm_sm100.cu)
     int l2_blocked_rerank = 0;  // opt-in: cuts the rerank's DRAM bytes 10 x but is 2 x slower (see kernels_basic.cu)
     int small_m128 = 0;  // measured slower than the CTA-pair tiles (5.9 vs 4.6 ms at 128 queries x 10M rows): off
@@ -453,9 +454,14 @@ int search_exact(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D
 }
 
 // ---- tensor path --------------------------------------------------------------------------
-int candidate_capacity(int k) {
+// Candidate-list slots per query.  A small database searched for many neighbours (k >= 256 of <= 16,384 rows: C2,
+// 14,433 rows, k = 1000) gets one slot per row: with k / N of 7 % a threshold filter lets a quarter of the scores of
+// its second panel through - tens of millions of atomic appends - so the whole database is scored as ONE dense panel
+// instead (plain coalesced stores), followed by one tighten (measured: C2's GEMM launches 2.9 -> ~0.6 ms).
+int candidate_capacity(int k, int64_t ntotal, bool dense_small) {
     int cap = 8192;
     while (cap < 8 * k) cap *= 2;
+    if (dense_small && k >= 256 && ntotal > cap && ntotal <= 16384) cap = 16384;
     return cap;
 }
 
@@ -507,6 +513,7 @@ int tensor_filter_batch(knn_index* ix, knn_index::TensorWs& W, int64_t off, int6
     int64_t first_panel = std::max<int64_t>(1024, round_up(4 * int64_t(k), 256));
     if (first_panel > cap / 2) first_panel = cap / 2;
     if (first_panel > N) first_panel = N;
+    if (ix->dense_small_db && k >= 256 && N <= cap && N <= 16384) first_panel = N;  // one dense panel: no later panel needs room
     // small batches are launch-bound, not list-bound: fewer, faster growing panels (7 k' survivors per panel and query)
     // (only while the ~7 k' survivors of the second panel fit next to the dense first panel: k' ~ 1.7 k)
     const bool fast_growth = nb <= ix->small_batch_nq && 12 * int64_t(k) + first_panel <= cap;
@@ -733,7 +740,7 @@ int redo_overflowed_host(knn_index* ix, int64_t nq, int64_t qb, int64_t nbatches
 // `hp` (host-pointer search): xq_dev / D / I are then HOST pointers that only the pipe touches.
 int search_tensor(knn_index* ix, int64_t nq, const float* xq_dev, int k, float* D, int64_t* I, int64_t id_base,
                   cudaStream_t s, HostPipe* hp = nullptr) {
-    const int cap = candidate_capacity(k);
+    const int cap = candidate_capacity(k, ix->ntotal, ix->dense_small_db != 0);
     int64_t qb = ix->query_batch;
     if (qb > nq) qb = nq;
     // A call that fits one batch has nothing to overlap its finish phase with.  Where that phase is heavy (k >= 256:
@@ -1212,7 +1219,7 @@ static int two_phase_begin(knn_index* ix, int64_t nq, const float* xq_dev, int64
         return KNN_OK;
     }
     KNN_CHECK(prepare_shadow(ix, k, s));
-    P.cap = candidate_capacity(k);
+    P.cap = candidate_capacity(k, ix->ntotal, ix->dense_small_db != 0);
     P.qb = round_up(std::min<int64_t>(ix->query_batch, nq), 256);
     P.nbatches = (nq + P.qb - 1) / P.qb;
     KNN_CHECK(tensor_ws_ensure(ix->ws2, P.nbatches * P.qb, ix->dp, P.cap));
@@ -1416,6 +1423,7 @@ int knn_index_set_param(knn_index* ix, const char* name, int64_t value) {
     else if (n == "overlap_finish") ix->overlap_finish = value != 0;
     else if (n == "small_m128") ix->small_m128 = value != 0;
     else if (n == "stream_pair") ix->stream_pair = value != 0;
+    else if (n == "dense_small_db") ix->dense_small_db = value != 0;
     else if (n == "stream_quad") ix->stream_quad = value != 0;
     else if (n == "l2_blocked_rerank") ix->l2_blocked_rerank = value != 0;
     else if (n == "split_single_batch") ix->split_single_batch = value != 0;

@@ -656,7 +656,7 @@ def test_l2_blocked_rerank_and_overlapped_batches_change_nothing(knn, metric):
     k = 300
     D1, I1, _ = _search(knn, xq[:600], xb, k, metric, path=1)
     base = None
-    for switches in ({}, {"l2_blocked_rerank": 0}, {"overlap_finish": 0}, {"split_single_batch": 0},
+    for switches in ({}, {"l2_blocked_rerank": 1}, {"overlap_finish": 0}, {"split_single_batch": 0},
                      {"query_batch": 1024}, {"query_batch": 1024, "overlap_finish": 0, "l2_blocked_rerank": 0}):
         D, I, idx = _search(knn, xq, xb, k, metric, path=2, **switches)
         assert idx.stat("path") == 2 and idx.stat("overflow_batches") == 0, switches
@@ -675,3 +675,22 @@ def test_l2_blocked_rerank_and_overlapped_batches_change_nothing(knn, metric):
     idx.add(xb)
     Dd, Id = idx.search(torch.from_numpy(xq).cuda(), k)
     assert np.array_equal(Id.cpu().numpy(), base[1]) and np.array_equal(Dd.cpu().numpy(), base[0])
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_small_database_large_k_single_dense_panel(knn, metric):
+    """k >= 256 of <= 16,384 rows (C2: 14,433 rows, k = 1000): the whole database is scored as one dense panel (one
+    candidate slot per row) instead of letting a quarter of the second panel's scores through the threshold filter.
+    Same bits as with the switch off and as the exact scan; duplicates and k close to N included."""
+    xq, xb = _data(1500, 14433, 256, seed=5, normalize=metric == IP)
+    xb[9000:9050] = xb[17]
+    for k in (256, 1000, 2048):
+        D1, I1, _ = _search(knn, xq[:300], xb, k, metric, path=1)
+        for on in (1, 0):
+            D, I, idx = _search(knn, xq, xb, k, metric, path=2, dense_small_db=on)
+            assert idx.stat("path") == 2 and idx.stat("overflow_batches") == 0, (k, on)
+            assert np.array_equal(I[:300], I1) and np.array_equal(D[:300], D1), (k, on)
+            if on:
+                launches_on = idx.stat("gemm_launches")
+            else:
+                assert idx.stat("gemm_launches") > launches_on  # several panels without the switch, one per batch with it
